@@ -1,0 +1,601 @@
+// tcrt_api.cu — the C ABI of include/tcrt.h: contexts, scene upload, render launches,
+// copy-back, the .txt writer.  No CPU render path exists here: without a CUDA device every
+// entry point that needs one fails.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "tcrt_device.h"
+
+namespace {
+
+struct DeviceState {
+    int dev = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_c1 = nullptr;
+    // scene
+    float4* scene_mem = nullptr;
+    size_t scene_cap_f4 = 0;
+    DeviceScene ds{};
+    // frame (band) + queue/counters
+    float* frame = nullptr;
+    size_t frame_cap = 0;   // floats
+    int x0 = 0, x1 = 0, height = 0;
+    unsigned char* ctl = nullptr;             // 64 B: queue head @0, counters @8..31
+    unsigned long long* h_counters = nullptr; // pinned, 4 x u64 (slot 0 unused)
+    // txt scratch
+    char* text = nullptr;
+    size_t text_cap = 0;
+    unsigned long long* offs = nullptr;
+    size_t offs_cap = 0;
+    unsigned long long* block_sums = nullptr;
+    size_t bs_cap = 0;
+    unsigned int* flag = nullptr;             // device, 4 B
+    unsigned long long* h_txt = nullptr;      // pinned: [0] flag, [1] total bytes
+    bool txt_fixed = true;
+    size_t txt_bytes = 0;
+    // L2 flush scratch
+    void* flush = nullptr;
+    size_t flush_bytes = 0;
+};
+
+}  // namespace
+
+struct tcrt_ctx {
+    std::vector<DeviceState> devs;
+    std::string err;
+    bool has_scene = false;
+    bool has_frame = false;
+    bool txt_prepared = false;
+    int frame_x0 = 0, frame_x1 = 0, frame_h = 0;
+    tcrt_camera cam{};           // passed by value with every launch
+    char* host_text = nullptr;   // pinned staging for tcrt_write_txt
+    size_t host_text_cap = 0;
+};
+
+namespace {
+
+thread_local std::string g_err = "";
+
+int fail(tcrt_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    g_err = buf;
+    return code;
+}
+
+#define CK(ctx, call)                                                                                        \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess)                                                                               \
+            return fail(ctx, TCRT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                        __LINE__);                                                                           \
+    } while (0)
+
+template <typename T>
+int ensure(tcrt_ctx* ctx, T*& p, size_t& cap, size_t need) {
+    if (need <= cap && p) return TCRT_OK;
+    if (p) CK(ctx, cudaFree(p));
+    p = nullptr;
+    cap = 0;
+    CK(ctx, cudaMalloc((void**)&p, need * sizeof(T)));
+    cap = need;
+    return TCRT_OK;
+}
+
+void free_device(DeviceState& d) {
+    if (d.dev < 0) return;
+    cudaSetDevice(d.dev);
+    if (d.stream) cudaStreamSynchronize(d.stream);
+    cudaFree(d.scene_mem);
+    cudaFree(d.frame);
+    cudaFree(d.ctl);
+    cudaFree(d.text);
+    cudaFree(d.offs);
+    cudaFree(d.block_sums);
+    cudaFree(d.flag);
+    cudaFree(d.flush);
+    cudaFreeHost(d.h_counters);
+    cudaFreeHost(d.h_txt);
+    if (d.ev_k0) cudaEventDestroy(d.ev_k0);
+    if (d.ev_k1) cudaEventDestroy(d.ev_k1);
+    if (d.ev_c1) cudaEventDestroy(d.ev_c1);
+    if (d.stream) cudaStreamDestroy(d.stream);
+    d = DeviceState{};
+}
+
+bool valid_params(const tcrt_params* p) {
+    return p && p->width > 0 && p->height > 0 && p->max_depth >= 0 &&
+           (long long)p->width * (long long)p->height <= 0x7fffffffLL / 3;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tcrt_abi_version(void) { return TCRT_ABI_VERSION; }
+
+void tcrt_default_params(tcrt_params* p) {
+    if (!p) return;
+    p->width = 500;
+    p->height = 504;
+    p->max_depth = 50;
+    p->shadows_on = 1;
+    p->reflections_on = 1;
+    p->null_color[0] = p->null_color[1] = p->null_color[2] = 0.75f;
+    p->far_dist = 65535.0f;
+}
+
+int tcrt_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, TCRT_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    return n;
+}
+
+const char* tcrt_last_error(tcrt_ctx* ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+void* tcrt_alloc_host(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void tcrt_free_host(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int tcrt_create(tcrt_ctx** out, const int* device_ids, int n_devices) {
+    if (!out || n_devices < 1 || n_devices > TCRT_MAX_DEVICES) return fail(nullptr, TCRT_ERR_INVALID, "bad arguments");
+    *out = nullptr;
+    int avail = tcrt_device_count();
+    if (avail <= 0) return fail(nullptr, TCRT_ERR_NO_DEVICE, "no CUDA device available (%s)", g_err.c_str());
+    tcrt_ctx* ctx = new tcrt_ctx();
+    ctx->devs.resize(n_devices);
+    for (int i = 0; i < n_devices; i++) {
+        int dev = device_ids ? device_ids[i] : i;
+        if (dev < 0 || dev >= avail) {
+            tcrt_destroy(ctx);
+            return fail(nullptr, TCRT_ERR_NO_DEVICE, "device %d out of range (have %d)", dev, avail);
+        }
+        DeviceState& d = ctx->devs[i];
+        d.dev = dev;
+        cudaError_t e = cudaSetDevice(dev);
+        cudaDeviceProp prop;
+        if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, dev);
+        if (e == cudaSuccess && prop.major < 10) {
+            tcrt_destroy(ctx);
+            return fail(nullptr, TCRT_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", dev,
+                        prop.major, prop.minor);
+        }
+        if (e == cudaSuccess) d.sm_count = prop.multiProcessorCount;
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreate(&d.ev_k0);
+        if (e == cudaSuccess) e = cudaEventCreate(&d.ev_k1);
+        if (e == cudaSuccess) e = cudaEventCreate(&d.ev_c1);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&d.ctl, 64);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&d.flag, 16);
+        if (e == cudaSuccess) e = cudaHostAlloc((void**)&d.h_counters, 64, cudaHostAllocPortable);
+        if (e == cudaSuccess) e = cudaHostAlloc((void**)&d.h_txt, 64, cudaHostAllocPortable);
+        if (e != cudaSuccess) {
+            std::string msg = cudaGetErrorString(e);
+            tcrt_destroy(ctx);
+            return fail(nullptr, TCRT_ERR_CUDA, "device %d setup failed: %s", dev, msg.c_str());
+        }
+    }
+    *out = ctx;
+    return TCRT_OK;
+}
+
+void tcrt_destroy(tcrt_ctx* ctx) {
+    if (!ctx) return;
+    for (auto& d : ctx->devs) free_device(d);
+    if (ctx->host_text) cudaFreeHost(ctx->host_text);
+    delete ctx;
+}
+
+// ---- scene upload -----------------------------------------------------------------------------
+int tcrt_upload_scene(tcrt_ctx* ctx, const tcrt_scene* s, const tcrt_camera* cam) {
+    if (!ctx || !s || !cam) return fail(ctx, TCRT_ERR_INVALID, "null argument");
+    if (s->n_objects < 0 || s->n_spheres < 0 || s->n_fin_planes < 0 || s->n_inf_planes < 0 || s->n_lights < 0 ||
+        s->n_textures < 0 || s->n_spheres + s->n_fin_planes + s->n_inf_planes != s->n_objects)
+        return fail(ctx, TCRT_ERR_INVALID, "inconsistent scene counts");
+    const int n = s->n_objects;
+    auto is_light = [&](int obj) { return s->obj_info[4 * obj + 2] != 0; };
+    for (int i = 0; i < s->n_spheres; i++)
+        if (s->sphere_obj[i] < 0 || s->sphere_obj[i] >= n) return fail(ctx, TCRT_ERR_INVALID, "sphere_obj out of range");
+    for (int i = 0; i < s->n_fin_planes; i++)
+        if (s->fin_obj[i] < 0 || s->fin_obj[i] >= n) return fail(ctx, TCRT_ERR_INVALID, "fin_obj out of range");
+    for (int i = 0; i < s->n_inf_planes; i++)
+        if (s->inf_obj[i] < 0 || s->inf_obj[i] >= n) return fail(ctx, TCRT_ERR_INVALID, "inf_obj out of range");
+    for (int i = 0; i < s->n_lights; i++)
+        if (s->light_obj[i] < 0 || s->light_obj[i] >= n) return fail(ctx, TCRT_ERR_INVALID, "light_obj out of range");
+    for (int i = 0; i < n; i++)
+        if (s->obj_info[4 * i + 3] >= s->n_textures) return fail(ctx, TCRT_ERR_INVALID, "texture id out of range");
+
+    // per type: non-light primitives first (shadow sweeps stop there), lights last
+    auto order = [&](const int* objs, int cnt, std::vector<int>& perm, int& n_nl) {
+        perm.clear();
+        for (int i = 0; i < cnt; i++)
+            if (!is_light(objs[i])) perm.push_back(i);
+        n_nl = (int)perm.size();
+        for (int i = 0; i < cnt; i++)
+            if (is_light(objs[i])) perm.push_back(i);
+    };
+    std::vector<int> ps, pf, pi;
+    DeviceScene ds{};
+    ds.n_sph = s->n_spheres;
+    ds.n_fin = s->n_fin_planes;
+    ds.n_inf = s->n_inf_planes;
+    ds.n_lights = s->n_lights;
+    order(s->sphere_obj, s->n_spheres, ps, ds.n_sph_nl);
+    order(s->fin_obj, s->n_fin_planes, pf, ds.n_fin_nl);
+    order(s->inf_obj, s->n_inf_planes, pi, ds.n_inf_nl);
+
+    ds.fin_off = ds.n_sph;
+    ds.inf_off = ds.fin_off + 4 * ds.n_fin;
+    ds.light_off = ds.inf_off + ds.n_inf;
+    ds.idx_off = ds.light_off + 2 * ds.n_lights;
+    const int n_prims = ds.n_sph + ds.n_fin + ds.n_inf;
+    ds.blob_f4 = ds.idx_off + (n_prims + 3) / 4;
+    if ((size_t)ds.blob_f4 * sizeof(float4) > tcrt_render_max_smem())
+        return fail(ctx, TCRT_ERR_UNSUPPORTED, "scene needs %zu B of shared memory per CTA (limit %zu)",
+                    (size_t)ds.blob_f4 * sizeof(float4), tcrt_render_max_smem());
+
+    const size_t off_surface = (size_t)ds.blob_f4;
+    const size_t off_material = off_surface + n;
+    const size_t off_normals = off_material + n;
+    const size_t off_frame = off_normals + 2 * (size_t)n;
+    const size_t off_tex = off_frame + 3 * (size_t)ds.n_inf;
+    const size_t total_f4 = off_tex + 2 * (size_t)s->n_textures + 1;
+    std::vector<float4> host(total_f4, make_float4(0.f, 0.f, 0.f, 0.f));
+    auto f4 = [](const float* p) { return make_float4(p[0], p[1], p[2], p[3]); };
+    int* idx = reinterpret_cast<int*>(&host[ds.idx_off]);
+    for (int k = 0; k < ds.n_sph; k++) {
+        host[k] = f4(s->sphere_geom + 4 * ps[k]);
+        idx[k] = s->sphere_obj[ps[k]];
+    }
+    for (int k = 0; k < ds.n_fin; k++) {
+        for (int j = 0; j < 4; j++) host[ds.fin_off + 4 * k + j] = f4(s->fin_geom + 16 * pf[k] + 4 * j);
+        idx[ds.n_sph + k] = s->fin_obj[pf[k]];
+    }
+    for (int k = 0; k < ds.n_inf; k++) {
+        host[ds.inf_off + k] = f4(s->inf_geom + 16 * pi[k]);
+        for (int j = 0; j < 3; j++) host[off_frame + 3 * k + j] = f4(s->inf_geom + 16 * pi[k] + 4 * (j + 1));
+        idx[ds.n_sph + ds.n_fin + k] = s->inf_obj[pi[k]];
+    }
+    for (int l = 0; l < ds.n_lights; l++) {
+        const int lo = s->light_obj[l];
+        const float* og = s->obj_origin + 4 * lo;
+        const float* sf = s->obj_surface + 4 * lo;
+        // (position, intensity) (material colour, 0): what the light loop reads, RayTracer.cpp:540-563
+        host[ds.light_off + 2 * l] = make_float4(og[0], og[1], og[2], s->obj_material[4 * lo + 2]);
+        host[ds.light_off + 2 * l + 1] = make_float4(sf[0], sf[1], sf[2], 0.f);
+    }
+    for (int i = 0; i < n; i++) {
+        host[off_surface + i] = f4(s->obj_surface + 4 * i);
+        float4 m = f4(s->obj_material + 4 * i);
+        int flags = (s->obj_info[4 * i + 3] + 1) & 0x7fffffff;
+        if (is_light(i)) flags |= (int)0x80000000u;
+        memcpy(&m.w, &flags, sizeof(float));   // bit pattern, read back with __float_as_int
+        host[off_material + i] = m;
+        host[off_normals + 2 * i] = f4(s->obj_normals + 8 * i);
+        host[off_normals + 2 * i + 1] = f4(s->obj_normals + 8 * i + 4);
+    }
+    for (int t = 0; t < s->n_textures; t++) {
+        host[off_tex + 2 * t] = f4(s->textures + 8 * t);
+        host[off_tex + 2 * t + 1] = f4(s->textures + 8 * t + 4);
+    }
+
+    for (auto& d : ctx->devs) {
+        CK(ctx, cudaSetDevice(d.dev));
+        int rc = ensure(ctx, d.scene_mem, d.scene_cap_f4, total_f4);
+        if (rc) return rc;
+        CK(ctx, cudaMemcpyAsync(d.scene_mem, host.data(), total_f4 * sizeof(float4), cudaMemcpyHostToDevice, d.stream));
+        CK(ctx, cudaStreamSynchronize(d.stream));   // `host` is a temporary
+        d.ds = ds;
+        d.ds.blob = d.scene_mem;
+        d.ds.obj_surface = d.scene_mem + off_surface;
+        d.ds.obj_material = d.scene_mem + off_material;
+        d.ds.obj_normals = d.scene_mem + off_normals;
+        d.ds.inf_frame = d.scene_mem + off_frame;
+        d.ds.textures = d.scene_mem + off_tex;
+        d.ds.obj_info = nullptr;
+    }
+    ctx->cam = *cam;
+    ctx->has_scene = true;
+    ctx->has_frame = false;
+    ctx->txt_prepared = false;
+    return TCRT_OK;
+}
+
+
+// ---- render -------------------------------------------------------------------------------------
+static int render_impl(tcrt_ctx* ctx, const tcrt_params* p, int x0, int x1, float* host_band, tcrt_stats* stats) {
+    if (!ctx) return fail(ctx, TCRT_ERR_INVALID, "null ctx");
+    if (!valid_params(p)) return fail(ctx, TCRT_ERR_INVALID, "bad params");
+    if (x0 < 0 || x1 > p->width || x0 >= x1) return fail(ctx, TCRT_ERR_INVALID, "bad column range [%d,%d)", x0, x1);
+    if (p->max_depth > TCRT_MAX_DEPTH)
+        return fail(ctx, TCRT_ERR_UNSUPPORTED, "max_depth %d > TCRT_MAX_DEPTH %d", p->max_depth, TCRT_MAX_DEPTH);
+    if (!ctx->has_scene) return fail(ctx, TCRT_ERR_NO_SCENE, "tcrt_upload_scene has not been called");
+    const int nd = (int)ctx->devs.size();
+    const int cols = x1 - x0;
+    ctx->has_frame = false;
+    ctx->txt_prepared = false;
+    int launches = 0;
+    // one contiguous band of columns per device (x-major storage makes a band one slice)
+    for (int i = 0; i < nd; i++) {
+        DeviceState& d = ctx->devs[i];
+        d.x0 = x0 + (int)((long long)cols * i / nd);
+        d.x1 = x0 + (int)((long long)cols * (i + 1) / nd);
+        d.height = p->height;
+    }
+    for (int i = 0; i < nd; i++) {
+        DeviceState& d = ctx->devs[i];
+        if (d.x1 <= d.x0) continue;
+        CK(ctx, cudaSetDevice(d.dev));
+        const size_t n_floats = (size_t)(d.x1 - d.x0) * p->height * 3;
+        int rc = ensure(ctx, d.frame, d.frame_cap, n_floats);
+        if (rc) return rc;
+        CK(ctx, cudaMemsetAsync(d.ctl, 0, 64, d.stream));
+        RenderLaunch rl{};
+        rl.scene = d.ds;
+        rl.cam = ctx->cam;
+        rl.width = p->width;
+        rl.height = p->height;
+        rl.x0 = d.x0;
+        rl.x1 = d.x1;
+        rl.max_depth = p->max_depth;
+        rl.shadows_on = p->shadows_on;
+        rl.reflections_on = p->reflections_on;
+        rl.null_r = p->null_color[0];
+        rl.null_g = p->null_color[1];
+        rl.null_b = p->null_color[2];
+        rl.far_dist = p->far_dist;
+        rl.out = d.frame;
+        rl.queue = reinterpret_cast<unsigned int*>(d.ctl);
+        rl.counters = reinterpret_cast<unsigned long long*>(d.ctl + 8);
+        CK(ctx, cudaEventRecord(d.ev_k0, d.stream));
+        CK(ctx, tcrt_launch_render(rl, d.sm_count, d.stream, &launches));
+        CK(ctx, cudaEventRecord(d.ev_k1, d.stream));
+        CK(ctx, cudaMemcpyAsync(d.h_counters, d.ctl, 32, cudaMemcpyDeviceToHost, d.stream));
+        if (host_band) {
+            float* dst = host_band + (size_t)(d.x0 - x0) * p->height * 3;
+            CK(ctx, cudaMemcpyAsync(dst, d.frame, n_floats * sizeof(float), cudaMemcpyDeviceToHost, d.stream));
+        }
+        CK(ctx, cudaEventRecord(d.ev_c1, d.stream));
+    }
+    if (stats) memset(stats, 0, sizeof(*stats));
+    for (int i = 0; i < nd; i++) {
+        DeviceState& d = ctx->devs[i];
+        if (stats) {
+            stats->col_begin[i] = d.x0;
+            stats->col_end[i] = d.x1;
+        }
+        if (d.x1 <= d.x0) continue;
+        CK(ctx, cudaSetDevice(d.dev));
+        CK(ctx, cudaStreamSynchronize(d.stream));
+        if (stats) {
+            float ms = 0.f;
+            CK(ctx, cudaEventElapsedTime(&ms, d.ev_k0, d.ev_k1));
+            stats->render_ms[i] = ms;
+            CK(ctx, cudaEventElapsedTime(&ms, d.ev_k1, d.ev_c1));
+            stats->d2h_ms[i] = host_band ? ms : 0.0;
+            stats->rays_primary[i] = d.h_counters[1];
+            stats->rays_shadow[i] = d.h_counters[2];
+            stats->rays_reflect[i] = d.h_counters[3];
+        }
+    }
+    if (stats) {
+        stats->n_devices = nd;
+        stats->gpu_launches = (unsigned long long)launches;
+    }
+    ctx->has_frame = true;
+    ctx->frame_x0 = x0;
+    ctx->frame_x1 = x1;
+    ctx->frame_h = p->height;
+    return TCRT_OK;
+}
+
+int tcrt_render(tcrt_ctx* ctx, const tcrt_params* p, float* host_rgb, tcrt_stats* stats) {
+    if (!host_rgb) return fail(ctx, TCRT_ERR_INVALID, "null output buffer");
+    if (!p) return fail(ctx, TCRT_ERR_INVALID, "null params");
+    return render_impl(ctx, p, 0, p->width, host_rgb, stats);
+}
+int tcrt_render_columns(tcrt_ctx* ctx, const tcrt_params* p, int x0, int x1, float* host_rgb_band, tcrt_stats* stats) {
+    if (!host_rgb_band) return fail(ctx, TCRT_ERR_INVALID, "null output buffer");
+    return render_impl(ctx, p, x0, x1, host_rgb_band, stats);
+}
+int tcrt_render_device(tcrt_ctx* ctx, const tcrt_params* p, int x0, int x1, tcrt_stats* stats) {
+    return render_impl(ctx, p, x0, x1, nullptr, stats);
+}
+
+int tcrt_download(tcrt_ctx* ctx, float* host_band) {
+    if (!ctx || !host_band) return fail(ctx, TCRT_ERR_INVALID, "null argument");
+    if (!ctx->has_frame) return fail(ctx, TCRT_ERR_NO_FRAME, "nothing rendered yet");
+    for (auto& d : ctx->devs) {
+        if (d.x1 <= d.x0) continue;
+        CK(ctx, cudaSetDevice(d.dev));
+        const size_t n_floats = (size_t)(d.x1 - d.x0) * d.height * 3;
+        float* dst = host_band + (size_t)(d.x0 - ctx->frame_x0) * d.height * 3;
+        CK(ctx, cudaMemcpyAsync(dst, d.frame, n_floats * sizeof(float), cudaMemcpyDeviceToHost, d.stream));
+    }
+    for (auto& d : ctx->devs) {
+        if (d.x1 <= d.x0) continue;
+        CK(ctx, cudaSetDevice(d.dev));
+        CK(ctx, cudaStreamSynchronize(d.stream));
+    }
+    return TCRT_OK;
+}
+
+int tcrt_device_frame(tcrt_ctx* ctx, int slot, void** dev_ptr, size_t* n_floats) {
+    if (!ctx || slot < 0 || slot >= (int)ctx->devs.size() || !dev_ptr || !n_floats)
+        return fail(ctx, TCRT_ERR_INVALID, "bad argument");
+    if (!ctx->has_frame) return fail(ctx, TCRT_ERR_NO_FRAME, "nothing rendered yet");
+    DeviceState& d = ctx->devs[slot];
+    *dev_ptr = d.frame;
+    *n_floats = (size_t)(d.x1 - d.x0) * d.height * 3;
+    return TCRT_OK;
+}
+
+int tcrt_flush_l2(tcrt_ctx* ctx) {
+    if (!ctx) return fail(ctx, TCRT_ERR_INVALID, "null ctx");
+    const size_t bytes = (size_t)256 << 20;   // > the 126 MB L2
+    for (auto& d : ctx->devs) {
+        CK(ctx, cudaSetDevice(d.dev));
+        if (!d.flush) {
+            CK(ctx, cudaMalloc(&d.flush, bytes));
+            d.flush_bytes = bytes;
+        }
+        CK(ctx, tcrt_launch_l2_flush(d.flush, d.flush_bytes, d.stream));
+    }
+    for (auto& d : ctx->devs) {
+        CK(ctx, cudaSetDevice(d.dev));
+        CK(ctx, cudaStreamSynchronize(d.stream));
+    }
+    return TCRT_OK;
+}
+
+// ---- .txt writer -----------------------------------------------------------------------------------
+// Decide fixed/general per device and size the output.
+static int prepare_txt(tcrt_ctx* ctx) {
+    if (!ctx->has_frame) return fail(ctx, TCRT_ERR_NO_FRAME, "nothing rendered yet");
+    if (ctx->txt_prepared) return TCRT_OK;
+    for (auto& d : ctx->devs) {
+        if (d.x1 <= d.x0) { d.txt_bytes = 0; continue; }
+        CK(ctx, cudaSetDevice(d.dev));
+        const size_t np = (size_t)(d.x1 - d.x0) * d.height;
+        CK(ctx, cudaMemsetAsync(d.flag, 0, 4, d.stream));
+        CK(ctx, tcrt_launch_txt_fixed_check(d.frame, np, d.flag, d.stream));
+        CK(ctx, cudaMemcpyAsync(d.h_txt, d.flag, 4, cudaMemcpyDeviceToHost, d.stream));
+    }
+    for (auto& d : ctx->devs) {
+        if (d.x1 <= d.x0) continue;
+        CK(ctx, cudaSetDevice(d.dev));
+        CK(ctx, cudaStreamSynchronize(d.stream));
+        const size_t np = (size_t)(d.x1 - d.x0) * d.height;
+        d.txt_fixed = (*(volatile unsigned int*)d.h_txt) == 0u;
+        if (d.txt_fixed) {
+            d.txt_bytes = np * 31;
+        } else {
+            const size_t nb = (np + 255) / 256;
+            int rc = ensure(ctx, d.offs, d.offs_cap, np);
+            if (rc) return rc;
+            rc = ensure(ctx, d.block_sums, d.bs_cap, nb + 1);
+            if (rc) return rc;
+            int launches = 0;
+            CK(ctx, tcrt_launch_txt_lengths(d.frame, np, d.offs, d.block_sums, d.stream, &launches));
+            CK(ctx, cudaMemcpyAsync(d.h_txt + 1, d.block_sums + nb, 8, cudaMemcpyDeviceToHost, d.stream));
+            CK(ctx, cudaStreamSynchronize(d.stream));
+            d.txt_bytes = (size_t)d.h_txt[1];
+        }
+    }
+    ctx->txt_prepared = true;
+    return TCRT_OK;
+}
+
+int tcrt_txt_size(tcrt_ctx* ctx, size_t* n_bytes) {
+    if (!ctx || !n_bytes) return fail(ctx, TCRT_ERR_INVALID, "null argument");
+    int rc = prepare_txt(ctx);
+    if (rc) return rc;
+    size_t t = 0;
+    for (auto& d : ctx->devs) t += d.txt_bytes;
+    *n_bytes = t;
+    return TCRT_OK;
+}
+
+int tcrt_format_txt(tcrt_ctx* ctx, char* host_text, size_t cap, size_t* n_bytes) {
+    if (!ctx || !host_text) return fail(ctx, TCRT_ERR_INVALID, "null argument");
+    size_t total = 0;
+    int rc = tcrt_txt_size(ctx, &total);
+    if (rc) return rc;
+    if (total > cap) return fail(ctx, TCRT_ERR_INVALID, "text needs %zu bytes, buffer has %zu", total, cap);
+    size_t off = 0;
+    for (auto& d : ctx->devs) {
+        if (d.x1 <= d.x0) continue;
+        CK(ctx, cudaSetDevice(d.dev));
+        const size_t np = (size_t)(d.x1 - d.x0) * d.height;
+        rc = ensure(ctx, d.text, d.text_cap, d.txt_bytes + 16);
+        if (rc) return rc;
+        if (d.txt_fixed) {
+            CK(ctx, tcrt_launch_txt_fixed(d.frame, np, d.text, d.stream));
+        } else {
+            CK(ctx, tcrt_launch_txt_general(d.frame, np, d.offs, d.block_sums, d.text, d.stream));
+        }
+        CK(ctx, cudaMemcpyAsync(host_text + off, d.text, d.txt_bytes, cudaMemcpyDeviceToHost, d.stream));
+        off += d.txt_bytes;
+    }
+    for (auto& d : ctx->devs) {
+        if (d.x1 <= d.x0) continue;
+        CK(ctx, cudaSetDevice(d.dev));
+        CK(ctx, cudaStreamSynchronize(d.stream));
+    }
+    if (n_bytes) *n_bytes = total;
+    return TCRT_OK;
+}
+
+int tcrt_txt_header(const tcrt_params* p, double run_time_s, char* buf, size_t cap) {
+    if (!p || !buf || cap == 0) return TCRT_ERR_INVALID;
+    // init_log (RayTracer.cpp:2033-2058) then the three tags of printPixelsToLog (:1576-1578);
+    // addToLogInt "%i", addToLogDouble "%f" (:2070-2096).  us/pixel = run_time_us / (W*H) with an
+    // int product (:1577).
+    const double us_per_pixel = (run_time_s * 1.0E6) / (p->width * p->height);
+    int n = snprintf(buf, cap,
+                     "OSX Awesome Picture\n"
+                     "Horizontal_Resolution:%i.\n"
+                     "Vertical_Resolution:%i.\n"
+                     "Hardware_Target:OSX C++.\n"
+                     "Number_of_Cores:%i.\n"
+                     "IS_FOR_HARDWARE\n"
+                     "NO_PARTIONING\n"
+                     "Run_Time:%f.\n"
+                     "us/pixel:%f.\n"
+                     "filename:raytracer_screen.txt.\n",
+                     p->width, p->height, 1, run_time_s, us_per_pixel);
+    if (n < 0 || (size_t)n >= cap) return TCRT_ERR_INVALID;
+    return n;
+}
+
+int tcrt_write_txt(tcrt_ctx* ctx, const tcrt_params* p, const char* path, double run_time_s) {
+    if (!ctx || !p || !path) return fail(ctx, TCRT_ERR_INVALID, "null argument");
+    if (!ctx->has_frame) return fail(ctx, TCRT_ERR_NO_FRAME, "nothing rendered yet");
+    if (ctx->frame_x0 != 0 || ctx->frame_x1 != p->width || ctx->frame_h != p->height)
+        return fail(ctx, TCRT_ERR_INVALID, "last render covered columns [%d,%d) x %d, not the %dx%d image", ctx->frame_x0,
+                    ctx->frame_x1, ctx->frame_h, p->width, p->height);
+    size_t total = 0;
+    int rc = tcrt_txt_size(ctx, &total);
+    if (rc) return rc;
+    if (total + 16 > ctx->host_text_cap) {
+        if (ctx->host_text) cudaFreeHost(ctx->host_text);
+        ctx->host_text = nullptr;
+        ctx->host_text_cap = 0;
+        CK(ctx, cudaHostAlloc((void**)&ctx->host_text, total + 16, cudaHostAllocPortable));
+        ctx->host_text_cap = total + 16;
+    }
+    rc = tcrt_format_txt(ctx, ctx->host_text, ctx->host_text_cap, &total);
+    if (rc) return rc;
+    char header[512];
+    int hn = tcrt_txt_header(p, run_time_s, header, sizeof header);
+    if (hn < 0) return fail(ctx, TCRT_ERR_INVALID, "header formatting failed");
+    FILE* f = fopen(path, "w");   // log_file_mode "w", RayTracer.h:135
+    if (!f) return fail(ctx, TCRT_ERR_IO, "Error Opening File %s", path);
+    bool ok = fwrite(header, 1, (size_t)hn, f) == (size_t)hn && fwrite(ctx->host_text, 1, total, f) == total;
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) return fail(ctx, TCRT_ERR_IO, "short write to %s", path);
+    return TCRT_OK;
+}
+
+}  // extern "C"

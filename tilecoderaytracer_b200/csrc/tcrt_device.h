@@ -1,0 +1,72 @@
+// tcrt_device.h — internal: structures shared by the CUDA kernels and the C-ABI layer.
+#ifndef TCRT_DEVICE_H_
+#define TCRT_DEVICE_H_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tcrt.h"
+
+// ---- device-resident scene ---------------------------------------------------------------
+// One allocation per device.  The "sweep blob" is what every CTA stages into shared memory
+// with coalesced float4 loads; everything else is winner-only data read through the
+// read-only path.
+//
+// Sweep blob layout (float4 units):
+//   [0, n_sph)                      sphere   (cx, cy, cz, r^2)
+//   [fin_off, fin_off + 4*n_fin)    finite   (n, -dto) (h, h_dist) (v, v_dist) (plane_origin, 0)
+//   [inf_off, inf_off + n_inf)      infinite (n, -dto)
+//   [light_off, light_off + 2*n_lights)  (light position, intensity) (light colour, 0)
+//   [idx_off, ...)                  int32 object index per primitive: spheres, finite, infinite
+// Within each type the non-light primitives come first (counts *_nl): the shadow sweep
+// (inShadeCollisionDetection skips lights, RayTracer.cpp:727) just stops there.  The
+// nearest-hit order inside a type is irrelevant because ties are resolved on the object
+// index explicitly.
+struct DeviceScene {
+    const float4* blob;        // sweep blob (global)
+    int blob_f4;               // size in float4 units (including the index tail, rounded up)
+    int n_sph, n_fin, n_inf;
+    int n_sph_nl, n_fin_nl, n_inf_nl;   // non-light prefix lengths
+    int n_lights;
+    int fin_off, inf_off, light_off, idx_off;   // float4 offsets into the blob
+    // winner-only, indexed by object index
+    const float4* obj_surface;   // colour rgb, diffuse
+    const float4* obj_material;  // specular, reflective, intensity, 0
+    const float4* obj_normals;   // 2 per object: facing normal, reverse normal
+    const int4* obj_info;        // type, slot (position in the permuted type array), is_light, texture id
+    const float4* inf_frame;     // 3 per infinite plane slot: horizontal, vertical, origin
+    const float4* textures;      // 2 per texture: (light rgb, width) (dark rgb, height)
+};
+
+struct RenderLaunch {
+    DeviceScene scene;
+    tcrt_camera cam;
+    int width, height;
+    int x0, x1;              // columns rendered by this launch
+    int max_depth;
+    int shadows_on, reflections_on;
+    float null_r, null_g, null_b;
+    float far_dist;
+    float* out;              // (x1-x0)*height*3 floats, x-major
+    unsigned int* queue;     // pixel queue head (zeroed before launch)
+    unsigned long long* counters;   // [0] primary [1] shadow [2] reflect
+    unsigned int chunk;      // pixels a warp claims per atomic
+};
+
+// render kernels (tcrt_render.cu)
+cudaError_t tcrt_launch_render(const RenderLaunch& rl, int sm_count, cudaStream_t stream, int* launches);
+size_t tcrt_render_max_smem();   // dynamic shared memory the kernel may opt in to
+
+// txt formatter (tcrt_format.cu)
+// fixed path: 31-byte lines; general path: per-pixel lengths -> two-level exclusive scan
+// (offs: n_pixels uint64 tile-local offsets; block_sums: ceil(n/256)+1 uint64, last = total).
+cudaError_t tcrt_launch_txt_fixed_check(const float* rgb, size_t n_pixels, unsigned int* not_fixed_flag,
+                                        cudaStream_t stream);
+cudaError_t tcrt_launch_txt_fixed(const float* rgb, size_t n_pixels, char* text, cudaStream_t stream);
+cudaError_t tcrt_launch_txt_lengths(const float* rgb, size_t n_pixels, unsigned long long* offs,
+                                    unsigned long long* block_sums, cudaStream_t stream, int* launches);
+cudaError_t tcrt_launch_txt_general(const float* rgb, size_t n_pixels, const unsigned long long* offs,
+                                    const unsigned long long* block_offs, char* text, cudaStream_t stream);
+cudaError_t tcrt_launch_l2_flush(void* scratch, size_t bytes, cudaStream_t stream);
+
+#endif  // TCRT_DEVICE_H_

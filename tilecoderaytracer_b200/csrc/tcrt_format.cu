@@ -1,0 +1,276 @@
+// tcrt_format.cu — the .txt writer's pixel lines on the GPU.
+//
+// Replaces the loop of printPixelsToLog (RayTracer.cpp:1589-1602):
+//     sprintf(line_str, "(%f, %f, %f)\n", temp->r, temp->g, temp->b); fputs(line_str, log_file);
+// Output is byte-identical to glibc's "%f" of the float promoted to double: the value is
+// M * 2^E exactly (M < 2^24), so  round_half_even(M * 10^6 * 2^E)  is computed in integers
+// (64-bit for E < 0; up to 128-bit for the integer part of huge values) — SURVEY §8a row W.
+//
+// Two paths:
+//   fixed   every channel prints as "d.dddddd" (0 <= v, rounds below 10): each line is exactly
+//           31 bytes.  A CTA formats 256 pixels into shared memory and streams the 7936 bytes
+//           out as 16-byte vectors.  This is every scene probed so far.
+//   general variable line lengths (values >= 10, negatives, inf/nan): per-pixel lengths,
+//           a two-level exclusive scan, then byte stores at the scanned offsets.
+#include "tcrt_device.h"
+
+namespace {
+
+constexpr int kFmtBlock = 256;
+constexpr int kLineFixed = 31;
+
+// round_half_even(|v| * 10^6) for |v| < 2^24 (E < 0 path); returns false when E >= 0.
+__device__ __forceinline__ bool micro_units(unsigned int bits, unsigned long long& q) {
+    unsigned int ex = (bits >> 23) & 0xffu;
+    unsigned int man = bits & 0x7fffffu;
+    unsigned int M = ex ? (man | 0x800000u) : man;
+    int E = (int)(ex ? ex : 1u) - 150;
+    if (E >= 0) return false;
+    int s = -E;
+    unsigned long long p = (unsigned long long)M * 1000000ull;   // < 2^44
+    if (s >= 46) {
+        q = 0;   // p < 2^44 <= 2^(s-2): below half a unit
+        return true;
+    }
+    q = p >> s;
+    unsigned long long rem = p & ((1ull << s) - 1ull);
+    unsigned long long half = 1ull << (s - 1);
+    if (rem > half || (rem == half && (q & 1ull))) ++q;
+    return true;
+}
+
+// True when v prints as exactly 8 characters "d.dddddd".
+__device__ __forceinline__ bool is_fixed8(float v, unsigned int& q_out) {
+    unsigned int bits = __float_as_uint(v);
+    if (bits >> 31) return false;                 // negatives (and -0) carry a sign
+    if (((bits >> 23) & 0xffu) == 0xffu) return false;
+    unsigned long long q;
+    if (!micro_units(bits, q)) return false;
+    if (q >= 10000000ull) return false;
+    q_out = (unsigned int)q;
+    return true;
+}
+
+__device__ __forceinline__ void put_fixed8(char* o, unsigned int q) {
+    unsigned int ip = q / 1000000u;
+    unsigned int fr = q - ip * 1000000u;
+    o[0] = (char)('0' + ip);
+    o[1] = '.';
+#pragma unroll
+    for (int k = 5; k >= 0; --k) {
+        unsigned int d = fr / 10u;
+        o[2 + k] = (char)('0' + (fr - d * 10u));
+        fr = d;
+    }
+}
+
+// General "%f": returns the length written to o (<= 47).
+__device__ int put_general(char* o, float v) {
+    unsigned int bits = __float_as_uint(v);
+    int n = 0;
+    if (bits >> 31) o[n++] = '-';
+    unsigned int ex = (bits >> 23) & 0xffu;
+    unsigned int man = bits & 0x7fffffu;
+    if (ex == 0xffu) {
+        const char* w = man ? "nan" : "inf";
+        o[n++] = w[0]; o[n++] = w[1]; o[n++] = w[2];
+        return n;
+    }
+    unsigned long long q;
+    unsigned int frac = 0;
+    char tmp[40];
+    int k = 0;
+    if (micro_units(bits, q)) {
+        unsigned long long ip = q / 1000000ull;
+        frac = (unsigned int)(q - ip * 1000000ull);
+        do { tmp[k++] = (char)('0' + (int)(ip % 10ull)); ip /= 10ull; } while (ip);
+    } else {
+        unsigned int M = man | 0x800000u;
+        int E = (int)ex - 150;
+        if (E <= 40) {
+            unsigned long long ip = (unsigned long long)M << E;
+            do { tmp[k++] = (char)('0' + (int)(ip % 10ull)); ip /= 10ull; } while (ip);
+        } else {
+            unsigned __int128 ip = (unsigned __int128)M << E;
+            do { tmp[k++] = (char)('0' + (int)(ip % 10)); ip /= 10; } while (ip);
+        }
+    }
+    while (k > 0) o[n++] = tmp[--k];
+    o[n++] = '.';
+    for (int j = 5; j >= 0; --j) {
+        unsigned int d = frac / 10u;
+        o[n + j] = (char)('0' + (frac - d * 10u));
+        frac = d;
+    }
+    return n + 6;
+}
+
+__device__ int line_general(char* o, float r, float g, float b) {
+    int n = 0;
+    o[n++] = '(';
+    n += put_general(o + n, r);
+    o[n++] = ','; o[n++] = ' ';
+    n += put_general(o + n, g);
+    o[n++] = ','; o[n++] = ' ';
+    n += put_general(o + n, b);
+    o[n++] = ')'; o[n++] = '\n';
+    return n;
+}
+
+// ---- fixed path ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kFmtBlock) txt_fixed_check_kernel(const float* __restrict__ rgb, size_t n_floats,
+                                                                    unsigned int* not_fixed) {
+    bool bad = false;
+    for (size_t i = blockIdx.x * (size_t)kFmtBlock + threadIdx.x; i < n_floats; i += (size_t)gridDim.x * kFmtBlock) {
+        unsigned int q;
+        if (!is_fixed8(rgb[i], q)) bad = true;
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(not_fixed, 1u);
+}
+
+__global__ void __launch_bounds__(kFmtBlock) txt_fixed_kernel(const float* __restrict__ rgb, size_t n_pixels,
+                                                              char* __restrict__ text) {
+    __shared__ __align__(16) char stage[kFmtBlock * kLineFixed];   // 7936 B = 496 x 16 B
+    __shared__ float in[kFmtBlock * 3];
+    const size_t n_tiles = (n_pixels + kFmtBlock - 1) / kFmtBlock;
+    for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const size_t p0 = tile * kFmtBlock;
+        const int np = (int)min((size_t)kFmtBlock, n_pixels - p0);
+        // coalesced load of np*3 floats
+        for (int i = threadIdx.x; i < np * 3; i += kFmtBlock) in[i] = rgb[p0 * 3 + i];
+        __syncthreads();
+        if ((int)threadIdx.x < np) {
+            char* o = stage + threadIdx.x * kLineFixed;
+            unsigned int q0 = 0, q1 = 0, q2 = 0;
+            is_fixed8(in[3 * threadIdx.x + 0], q0);
+            is_fixed8(in[3 * threadIdx.x + 1], q1);
+            is_fixed8(in[3 * threadIdx.x + 2], q2);
+            o[0] = '(';
+            put_fixed8(o + 1, q0);
+            o[9] = ','; o[10] = ' ';
+            put_fixed8(o + 11, q1);
+            o[19] = ','; o[20] = ' ';
+            put_fixed8(o + 21, q2);
+            o[29] = ')'; o[30] = '\n';
+        }
+        __syncthreads();
+        const size_t byte0 = p0 * kLineFixed;      // multiple of 7936 -> 16-byte aligned
+        const int nbytes = np * kLineFixed;
+        const int nvec = nbytes / 16;
+        uint4* dst = reinterpret_cast<uint4*>(text + byte0);
+        const uint4* src = reinterpret_cast<const uint4*>(stage);
+        for (int i = threadIdx.x; i < nvec; i += kFmtBlock) dst[i] = src[i];
+        for (int i = nvec * 16 + threadIdx.x; i < nbytes; i += kFmtBlock) text[byte0 + i] = stage[i];
+        __syncthreads();
+    }
+}
+
+// ---- general path ------------------------------------------------------------------------------
+// offs[i] = exclusive prefix of line lengths inside the tile; block_sums[tile] = tile total.
+__global__ void __launch_bounds__(kFmtBlock) txt_len_kernel(const float* __restrict__ rgb, size_t n_pixels,
+                                                            unsigned long long* __restrict__ offs,
+                                                            unsigned long long* __restrict__ block_sums) {
+    __shared__ unsigned int warp_tot[kFmtBlock / 32];
+    const size_t p = blockIdx.x * (size_t)kFmtBlock + threadIdx.x;
+    char scratch[160];
+    unsigned int len = 0;
+    if (p < n_pixels) len = (unsigned int)line_general(scratch, rgb[3 * p], rgb[3 * p + 1], rgb[3 * p + 2]);
+    unsigned int incl = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((threadIdx.x & 31) >= o) incl += t;
+    }
+    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    unsigned int base = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) base += warp_tot[w];
+    if (p < n_pixels) offs[p] = (unsigned long long)(base + incl - len);
+    if (threadIdx.x == kFmtBlock - 1) block_sums[blockIdx.x] = (unsigned long long)(base + incl);
+}
+
+// single CTA: exclusive scan of block_sums in place; total appended at block_sums[n]
+__global__ void __launch_bounds__(1024) txt_scan_kernel(unsigned long long* block_sums, size_t n) {
+    __shared__ unsigned long long warp_tot[32];
+    __shared__ unsigned long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (size_t i0 = 0; i0 < n; i0 += 1024) {
+        size_t i = i0 + threadIdx.x;
+        unsigned long long v = (i < n) ? block_sums[i] : 0ull;
+        unsigned long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((threadIdx.x & 31) >= o) incl += t;
+        }
+        if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        unsigned long long base = carry;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) base += warp_tot[w];
+        if (i < n) block_sums[i] = base + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = base + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) block_sums[n] = carry;
+}
+
+__global__ void __launch_bounds__(kFmtBlock) txt_general_kernel(const float* __restrict__ rgb, size_t n_pixels,
+                                                                const unsigned long long* __restrict__ offs,
+                                                                const unsigned long long* __restrict__ block_offs,
+                                                                char* __restrict__ text) {
+    const size_t p = blockIdx.x * (size_t)kFmtBlock + threadIdx.x;
+    if (p >= n_pixels) return;
+    char line[160];
+    int n = line_general(line, rgb[3 * p], rgb[3 * p + 1], rgb[3 * p + 2]);
+    char* o = text + block_offs[blockIdx.x] + offs[p];
+    for (int i = 0; i < n; ++i) o[i] = line[i];
+}
+
+__global__ void l2_flush_kernel(uint4* p, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        p[i] = make_uint4(0u, 1u, 2u, 3u);
+}
+
+}  // namespace
+
+cudaError_t tcrt_launch_txt_fixed_check(const float* rgb, size_t n_pixels, unsigned int* not_fixed_flag,
+                                        cudaStream_t stream) {
+    if (n_pixels == 0) return cudaSuccess;
+    txt_fixed_check_kernel<<<148 * 8, kFmtBlock, 0, stream>>>(rgb, n_pixels * 3, not_fixed_flag);
+    return cudaGetLastError();
+}
+
+cudaError_t tcrt_launch_txt_fixed(const float* rgb, size_t n_pixels, char* text, cudaStream_t stream) {
+    if (n_pixels == 0) return cudaSuccess;
+    size_t tiles = (n_pixels + kFmtBlock - 1) / kFmtBlock;
+    int grid = (int)min(tiles, (size_t)148 * 8);
+    txt_fixed_kernel<<<grid, kFmtBlock, 0, stream>>>(rgb, n_pixels, text);
+    return cudaGetLastError();
+}
+
+// offs: n_pixels uint64; block_sums: ceil(n_pixels/256) + 1 uint64.  After this,
+// block_sums[0..nb) are exclusive tile offsets and block_sums[nb] the total byte count.
+cudaError_t tcrt_launch_txt_lengths(const float* rgb, size_t n_pixels, unsigned long long* offs,
+                                    unsigned long long* block_sums, cudaStream_t stream, int* launches) {
+    if (n_pixels == 0) return cudaSuccess;
+    size_t nb = (n_pixels + kFmtBlock - 1) / kFmtBlock;
+    txt_len_kernel<<<(unsigned)nb, kFmtBlock, 0, stream>>>(rgb, n_pixels, offs, block_sums);
+    txt_scan_kernel<<<1, 1024, 0, stream>>>(block_sums, nb);
+    if (launches) *launches += 2;
+    return cudaGetLastError();
+}
+
+cudaError_t tcrt_launch_txt_general(const float* rgb, size_t n_pixels, const unsigned long long* offs,
+                                     const unsigned long long* block_offs, char* text, cudaStream_t stream) {
+    if (n_pixels == 0) return cudaSuccess;
+    size_t nb = (n_pixels + kFmtBlock - 1) / kFmtBlock;
+    txt_general_kernel<<<(unsigned)nb, kFmtBlock, 0, stream>>>(rgb, n_pixels, offs, block_offs, text);
+    return cudaGetLastError();
+}
+
+cudaError_t tcrt_launch_l2_flush(void* scratch, size_t bytes, cudaStream_t stream) {
+    l2_flush_kernel<<<148 * 4, 256, 0, stream>>>(reinterpret_cast<uint4*>(scratch), bytes / 16);
+    return cudaGetLastError();
+}
