@@ -179,6 +179,11 @@ int tcrt_download(tcrt_ctx* ctx, float* host_rgb_band);
 int tcrt_device_frame(tcrt_ctx* ctx, int device_slot, void** dev_ptr, size_t* n_floats);
 /* Overwrite the L2 cache of every device of the ctx (benchmark hygiene between timed steps). */
 int tcrt_flush_l2(tcrt_ctx* ctx);
+/* FP32-pipe microbenchmark on device slot 0 (the roofline denominator of this path, SURVEY
+ * §8d): sustained lane-operations per second of dependent-chain FMUL+FADD pairs (unfused, the
+ * instruction mix parity-exact code issues) and of FFMA, in units of 1e12 lane-instructions/s,
+ * plus the kernel time of each probe.  FFMA counts 1 instruction (2 flops). */
+int tcrt_fp32_peak(tcrt_ctx* ctx, double* unfused_tera_inst, double* fma_tera_inst, double* ms_each);
 
 /* ---- .txt writer (replaces init_log + printPixelsToLog) --------------------------- */
 /* Bytes of the pixel lines "(%f, %f, %f)\n" of the last render (all its columns). */
@@ -187,6 +192,11 @@ int tcrt_txt_size(tcrt_ctx* ctx, size_t* n_bytes);
  * cap bytes, no terminator); *n_bytes = length.  Byte-identical to glibc's
  * sprintf("(%f, %f, %f)\n") of the same floats (RayTracer.cpp:1601). */
 int tcrt_format_txt(tcrt_ctx* ctx, char* host_text, size_t cap, size_t* n_bytes);
+/* Same formatter applied to caller-supplied pixels (n_pixels*3 floats in host memory): H2D,
+ * format on device 0 of the ctx, D2H.  Independent of the last render (the reference's
+ * main_test, RayTracer.cpp:1412-1444, drives its writer this way). */
+int tcrt_format_pixels(tcrt_ctx* ctx, const float* host_rgb, size_t n_pixels, char* host_text, size_t cap,
+                       size_t* n_bytes);
 /* Header lines of the file (init_log RayTracer.cpp:2033-2058 + the three tag lines of
  * printPixelsToLog :1576-1578), x86 personality: "OSX Awesome Picture", Hardware_Target
  * "OSX C++", Number_of_Cores 1, IS_FOR_HARDWARE, NO_PARTIONING.  Returns length written

@@ -25,7 +25,10 @@ REF_RENDER = os.path.join(REF_DIR, "ref_render")
 
 class OracleCounters(C.Structure):
     _fields_ = [(n, C.c_ulonglong) for n in
-                ("rays_primary", "rays_shadow", "rays_reflect", "tests_sphere", "tests_fin", "tests_inf")]
+                ("rays_primary", "rays_shadow", "rays_reflect", "tests_sphere", "tests_fin", "tests_inf",
+                 "sph_exit_v", "sph_exit_d2", "sph_hit", "fin_exit_t", "fin_bounds",
+                 "hits_sphere", "hits_plane", "hits_reflective", "hits_textured", "hits_light", "misses",
+                 "lit_pairs", "lit_pairs_spec", "combines", "flops")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

@@ -47,10 +47,22 @@ static inline v3 v3_normalize(v3 a) {
     return v3_make(a.x / len, a.y / len, a.z / len);
 }
 
+/* Work counters.  The primitive tests are counted as the REFERENCE executes them: every object
+ * for a nearest-hit query (RayTracer.cpp:73-86), objects in index order up to the first blocker
+ * for a shadow query (:724-736) — see in_shade().  `flops` applies SURVEY.md §8(d)'s per-unit
+ * constants (add/sub/mul/div/sqrt/fmod = 1, negate/compare/select/convert = 0). */
 typedef struct {
     unsigned long long rays_primary, rays_shadow, rays_reflect;
     unsigned long long tests_sphere, tests_fin, tests_inf; /* executed primitive tests */
+    unsigned long long sph_exit_v, sph_exit_d2, sph_hit;   /* sphere test outcome classes */
+    unsigned long long fin_exit_t, fin_bounds;              /* finite plane: left at t / bounds evaluated */
+    unsigned long long hits_sphere, hits_plane, hits_reflective, hits_textured, hits_light, misses;
+    unsigned long long lit_pairs, lit_pairs_spec;           /* unshadowed (hit, light) pairs; with V.R > 0 */
+    unsigned long long combines;                            /* reflection combine steps */
+    unsigned long long flops;                               /* algorithmic flops, SURVEY §8(d) */
 } oracle_counters;
+
+static oracle_counters* g_cnt; /* current counters (single-threaded test code) */
 
 /* ---- primitive tests: distance only -------------------------------------------------- */
 
@@ -59,10 +71,11 @@ typedef struct {
 static inline int sphere_dist(const float* g, v3 O, v3 D, float* dist) {
     v3 OE = v3_sub(v3_ld(g), O);                        /* :54 */
     float v = v3_dot(OE, D);                            /* :56 */
-    if (v < 0.0f) return 0;                             /* :58 */
+    if (v < 0.0f) { g_cnt->sph_exit_v++; return 0; }    /* :58 */
     float d2 = g[3] - (v3_dot(OE, OE) - v * v);         /* :66 */
-    if (d2 < (float)1E-9) return 0;                     /* :68 */
+    if (d2 < (float)1E-9) { g_cnt->sph_exit_d2++; return 0; } /* :68 */
     *dist = v - sqrtf(d2);                              /* :85,:139 */
+    g_cnt->sph_hit++;
     return 1;
 }
 
@@ -82,8 +95,9 @@ static inline int plane_t(const float* g, v3 O, v3 D, float* t, float* den_out) 
  * coordinates (needed by the texture lookup of the winner). */
 static inline int fin_dist(const float* g, v3 O, v3 D, float* dist, float* px, float* py, float* den) {
     float t;
-    if (!plane_t(g, O, D, &t, den)) return 0;
-    if ((double)t < 1E-5) return 0;                     /* :102 — a double compare */
+    if (!plane_t(g, O, D, &t, den)) { g_cnt->fin_exit_t++; return 0; }
+    if ((double)t < 1E-5) { g_cnt->fin_exit_t++; return 0; } /* :102 — a double compare */
+    g_cnt->fin_bounds++;
     v3 P = v3_add(v3_scale(D, t), O);                   /* :108 */
     v3 PO = v3_sub(P, v3_ld(g + 12));                   /* :116 */
     float x = v3_dot(PO, v3_ld(g + 4));                 /* :119 */
@@ -206,23 +220,25 @@ static int nearest_hit(const tcrt_scene* s, const tcrt_params* p, v3 O, v3 D, fl
 }
 
 /* ---- inShadeCollisionDetection, RayTracer.cpp:709-739: any non-light object closer than
- * the light ------------------------------------------------------------------------------- */
+ * the light.  The answer does not depend on the order; the loop runs in object-index order
+ * with the reference's early exit so that the executed-test counters are the reference's. ---- */
 static int in_shade(const tcrt_scene* s, v3 O, v3 D, float dist_to_light, oracle_counters* c) {
     float d, x, y, den;
-    for (int i = 0; i < s->n_spheres; i++) {
-        if (s->obj_info[4 * s->sphere_obj[i] + 2]) continue;
-        c->tests_sphere++;
-        if (sphere_dist(s->sphere_geom + 4 * i, O, D, &d) && d < dist_to_light) return 1;
-    }
-    for (int i = 0; i < s->n_fin_planes; i++) {
-        if (s->obj_info[4 * s->fin_obj[i] + 2]) continue;
-        c->tests_fin++;
-        if (fin_dist(s->fin_geom + 16 * i, O, D, &d, &x, &y, &den) && d < dist_to_light) return 1;
-    }
-    for (int i = 0; i < s->n_inf_planes; i++) {
-        if (s->obj_info[4 * s->inf_obj[i] + 2]) continue;
-        c->tests_inf++;
-        if (inf_dist(s->inf_geom + 16 * i, O, D, &d, &den) && d < dist_to_light) return 1;
+    for (int obj = 0; obj < s->n_objects; obj++) {
+        const int* info = s->obj_info + 4 * obj;
+        if (info[2]) continue;                          /* :727 lights are skipped */
+        int hit;
+        if (info[0] == TCRT_SPHERE) {
+            c->tests_sphere++;
+            hit = sphere_dist(s->sphere_geom + 4 * info[1], O, D, &d);
+        } else if (info[0] == TCRT_FINITE_PLANE) {
+            c->tests_fin++;
+            hit = fin_dist(s->fin_geom + 16 * info[1], O, D, &d, &x, &y, &den);
+        } else {
+            c->tests_inf++;
+            hit = inf_dist(s->inf_geom + 16 * info[1], O, D, &d, &den);
+        }
+        if (hit && d < dist_to_light) return 1;         /* :729-731 */
     }
     return 0;
 }
@@ -245,6 +261,7 @@ static v3 shade_lights(const tcrt_scene* s, const tcrt_params* p, const hit_reco
             shaded = in_shade(s, h->P, lr, dist, c);
         }
         if (shaded) continue;
+        c->lit_pairs++;
         /* cosineShade, :654-701 (light_ray there equals lr) */
         if (h->diffuse > 0.0f) {
             float cdf = v3_dot(h->n2, lr);              /* :680 */
@@ -264,6 +281,7 @@ static v3 shade_lights(const tcrt_scene* s, const tcrt_params* p, const hit_reco
         v3 R = v3_sub(lr, v3_scale(N, two_ln));         /* L - 2.0f*L.dot(N)*N */
         float dot = v3_dot(V, R);
         if (dot > 0.0f) {
+            c->lit_pairs_spec++;
             float pw = dot;
             for (int i = 0; i < 19; i++) pw *= dot;     /* :581-584 */
             float spec = pw * h->specular;
@@ -288,9 +306,13 @@ static v3 trace_pixel(const tcrt_scene* s, const tcrt_params* p, v3 O, v3 D, lev
          * would be spawned, below */
         float dist, px, py, den;
         int obj = nearest_hit(s, p, O, D, &dist, &px, &py, &den, c);
-        if (obj < 0) { tail = null_color; break; }      /* :507-509 */
+        if (obj < 0) { c->misses++; tail = null_color; break; } /* :507-509 */
         hit_record h;
         build_hit(s, obj, dist, px, py, den, O, D, &h);
+        if (s->obj_info[4 * obj] == TCRT_SPHERE) c->hits_sphere++; else c->hits_plane++;
+        if (h.reflective_material) c->hits_reflective++;
+        if (s->obj_info[4 * obj + 3] >= 0) c->hits_textured++;
+        if (h.is_light) c->hits_light++;
         if (h.is_light) {                               /* :520-527 */
             tail = v3_scale(h.color, h.intensity);
             break;
@@ -313,6 +335,7 @@ static v3 trace_pixel(const tcrt_scene* s, const tcrt_params* p, v3 O, v3 D, lev
     }
     /* final_color += getReflectiveFactor() * reflective_color * object_color  (:601):
      * ((k * child) * obj), added to the level's local colour, deepest level first */
+    c->combines += (unsigned long long)depth;
     for (int i = depth - 1; i >= 0; i--) {
         v3 kc = v3_scale(tail, stack[i].k);
         tail.x = stack[i].local.x + kc.x * stack[i].obj.x;
@@ -344,6 +367,7 @@ int tcrt_oracle_render(const tcrt_scene* s, const tcrt_camera* cam, const tcrt_p
         return -1;
     oracle_counters c;
     memset(&c, 0, sizeof(c));
+    g_cnt = &c;
     level_rec* stack = (level_rec*)malloc(sizeof(level_rec) * (size_t)(p->max_depth + 2));
     if (!stack) return -1;
     size_t k = 0;
@@ -356,6 +380,17 @@ int tcrt_oracle_render(const tcrt_scene* s, const tcrt_camera* cam, const tcrt_p
             out[k++] = col.x; out[k++] = col.y; out[k++] = col.z;
         }
     free(stack);
+    /* SURVEY §8(d) per-unit constants */
+    c.flops = 30ull * c.rays_primary
+            + 8ull * c.sph_exit_v + 16ull * c.sph_exit_d2 + 18ull * c.sph_hit
+            + 12ull * c.tests_inf
+            + 12ull * c.fin_exit_t + 31ull * c.fin_bounds
+            + 32ull * c.hits_sphere + 31ull * c.hits_plane + 18ull * c.hits_reflective + 17ull * c.hits_textured
+            + 18ull * (s->n_lights > 0 ? (c.rays_shadow ? c.rays_shadow
+                                                        : (c.hits_sphere + c.hits_plane - c.hits_light) * (unsigned long long)s->n_lights)
+                                       : 0ull)
+            + 66ull * c.lit_pairs + 26ull * c.lit_pairs_spec
+            + 9ull * c.combines;
     if (counters) *counters = c;
     return 0;
 }

@@ -1,0 +1,334 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against
+  * the oracle (CPU restatement pinned to the reference) on the same inputs — bit-exact,
+  * the committed goldens made by the reference itself — bit-exact / md5-exact,
+  * size-independent properties at the BASELINE.json sizes.
+
+Stated tolerance of the north_star is <= 1 LSB per 8-bit channel on >= 99.9 % of pixels; the
+bar enforced here is stricter: identical float bit patterns on every pixel (all arithmetic is
+IEEE binary32, unfused, in the reference's order on both sides).
+"""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from oracle import oracle_py as O
+from tilecoderaytracer_b200 import _ffi, api
+from tilecoderaytracer_b200.partition import column_bands
+
+from _util import assert_bit_identical, bits, make_scene, n_mismatch, parse_txt, pixel_md5, quant8
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_and_oracle(ctx, scene_name, w, h, depth, **kw):
+    scene, cam = make_scene(scene_name)
+    params = api.default_params(w, h, depth, **kw)
+    ctx.upload(scene, cam)
+    img, stats = ctx.render(params)
+    want, cnt = O.render(scene.flatten(), cam.export(), params)
+    return img, stats, want, cnt
+
+
+def check_counters(stats, cnt):
+    assert stats.rays_primary == cnt["rays_primary"]
+    assert stats.rays_shadow == cnt["rays_shadow"]
+    assert stats.rays_reflect == cnt["rays_reflect"]
+
+
+# ---- against the oracle, same seeded inputs -------------------------------------------------------
+
+@pytest.mark.parametrize("scene,w,h,d", [
+    ("default", 500, 504, 50),        # BASELINE configs[0]
+    ("default", 320, 180, 5),         # configs[1] scaled
+    ("default", 97, 61, 0), ("default", 64, 48, 1), ("default", 64, 48, 200),
+    ("synth1024", 160, 128, 50),      # configs[3] scaled
+    ("synth256", 160, 128, 10),       # configs[4] scaled
+    ("two_mirrors", 96, 80, 50),      # the reference's SCENE 2
+])
+def test_named_scenes_bit_exact(gpu_ctx, scene, w, h, d):
+    img, stats, want, cnt = gpu_and_oracle(gpu_ctx, scene, w, h, d)
+    assert_bit_identical(img, want, f"{scene} {w}x{h} d{d}")
+    check_counters(stats, cnt)
+    assert stats.gpu_launches == 1
+    # the tolerance the north_star states, for the record
+    assert (np.abs(quant8(img) - quant8(want)) <= 1).all(axis=-1).mean() >= 0.999
+
+
+@pytest.mark.parametrize("seed,n", [(21, 12), (22, 40), (23, 90), (24, 200), (25, 600), (26, 33), (27, 1500), (28, 3)])
+def test_random_scenes_bit_exact(gpu_ctx, seed, n):
+    """Fuzz: every primitive type and ctor, lights of several types, textures, mirrors, diffuse-0."""
+    img, stats, want, cnt = gpu_and_oracle(gpu_ctx, f"random:{seed}:{n}", 112, 80, 9)
+    assert_bit_identical(img, want, f"random:{seed}:{n}")
+    check_counters(stats, cnt)
+
+
+def test_switches_shadows_reflections(gpu_ctx):
+    for kw in ({"shadows": False}, {"reflections": False}, {"shadows": False, "reflections": False}):
+        img, stats, want, cnt = gpu_and_oracle(gpu_ctx, "default", 120, 90, 7, **kw)
+        assert_bit_identical(img, want, str(kw))
+        check_counters(stats, cnt)
+
+
+def test_handmade_scene_edge_cases(gpu_ctx):
+    """Camera inside a sphere (negative distance wins, SceneSphere.cpp:139), a plane light, a
+    textured finite plane, coincident spheres (index tie-break, RayTracer.cpp:77), no lights."""
+    cam = api.Camera()
+    eye = np.array(cam.export().eye[:], np.float32)
+    for variant in range(4):
+        s = api.Scene()
+        if variant != 3:
+            s.addFinitePlaneCorners((2, 2, 9), (2, 2.5, 9), (2.5, 2, 9)).setAsLightSource(0.9)
+            s.addSphere((-6, 0, 8), .2).setAsLightSource(0.5).setColor(1, .5, .25)
+        if variant == 0:
+            s.addSphere(tuple(eye), 3.0).setColor(.2, .4, .9)            # we are inside this one
+        s.addSphere((0, 0, 1), 1.0).setColor(1, 0, 0).setReflectiveFactor(.7)
+        s.addSphere((0, 0, 1), 1.0).setColor(0, 1, 0)                   # coincident: the red one must win
+        s.addInfinitePlane((0, 0, 0), (0, 0, 1), (1, 0, 0)).setCheckerBoard((1, 1, 0), (0, 0, 1), 1.5, .7)
+        s.addFinitePlaneAxes((-1, 3, 0), (0, -1, 0), (1, 0, 0), 2.5, 3.0).setCheckerBoard((1, 1, 1), (.1, .1, .1), .5, .5) \
+            .setReflectiveFactor(.4).setDiffuseFactor(0.0)
+        if variant == 2:
+            for o in s.makeSceneBox((-3, -3, 0), (1, 1, 2)):
+                o.setColor(.6, .3, .1).setSpecularFactor(.3)
+        params = api.default_params(140, 100, 6)
+        gpu_ctx.upload(s, cam)
+        img, stats = gpu_ctx.render(params)
+        want, cnt = O.render(s.flatten(), cam.export(), params)
+        assert_bit_identical(img, want, f"handmade variant {variant}")
+        check_counters(stats, cnt)
+
+
+def test_empty_scene_and_tiny_images(gpu_ctx):
+    cam = api.Camera()
+    gpu_ctx.upload(api.Scene(), cam)
+    img, stats = gpu_ctx.render(api.default_params(33, 17, 4))
+    assert np.all(img == np.float32(0.75)) and stats.rays == 33 * 17
+    scene, cam = make_scene("default")
+    gpu_ctx.upload(scene, cam)
+    for w, h in [(1, 1), (1, 37), (37, 1), (2, 3)]:
+        p = api.default_params(w, h, 50)
+        img, stats = gpu_ctx.render(p)
+        want, _ = O.render(scene.flatten(), cam.export(), p)
+        assert_bit_identical(img, want, f"{w}x{h}")
+        assert stats.rays_primary == w * h
+
+
+def test_maximum_object_count(gpu_ctx):
+    """3999 objects = the most Scene::addObject accepts (Scene.cpp:470-479)."""
+    cam = api.Camera()
+    s = api.Scene()
+    s.addSphere((2, -3, 9), .2).setAsLightSource(1.0)
+    s.addInfinitePlane((0, 0, 0), (0, 0, 1), (1, 0, 0)).setCheckerBoard((1, 1, 1), (0, 0, 0), 3, 3)
+    k = 0
+    while s.getObjectCount() < 3999:
+        i, j, l = k % 20, (k // 20) % 20, k // 400
+        s.addSphere((-2 + .45 * i, .45 * j, .2 + .45 * l), .2).setColor((i % 3) / 2, (j % 3) / 2, (l % 3) / 2) \
+            .setReflectiveFactor(.5 if k % 7 == 0 else 0.0)
+        k += 1
+    assert s.getObjectCount() == 3999
+    gpu_ctx.upload(s, cam)
+    p = api.default_params(64, 48, 4)
+    img, stats = gpu_ctx.render(p)
+    want, cnt = O.render(s.flatten(), cam.export(), p)
+    assert_bit_identical(img, want, "3999 objects")
+    check_counters(stats, cnt)
+
+
+# ---- against the committed goldens (made by the reference itself) -------------------------------------
+
+def test_golden_frames_bit_exact(gpu_ctx, golden, golden_frames):
+    for key, m in golden["frames"].items():
+        scene, cam = make_scene(m["scene"])
+        gpu_ctx.upload(scene, cam)
+        img, _ = gpu_ctx.render(api.default_params(m["W"], m["H"], m["depth"]))
+        assert_bit_identical(img, golden_frames[key], key)
+
+
+@pytest.mark.parametrize("key", ["default_500x504_d50", "default_1920x1080_d5", "synth1024_500x504_d50",
+                                 "synth256_500x504_d10", "two_mirrors_500x504_d50", "random_4_80_200x160_d8",
+                                 "default_3840x2160_d50"])
+def test_txt_md5_matches_reference_file(gpu_ctx, golden, key):
+    """Render + GPU .txt formatter + file writer; md5 of the pixel lines equals the reference
+    program's.  default_500x504_d50 is the program exactly as checked in (rt_asis)."""
+    g = golden["md5"][key]
+    scene, cam = make_scene(g["scene"])
+    gpu_ctx.upload(scene, cam)
+    p = api.default_params(g["W"], g["H"], g["depth"])
+    gpu_ctx.render_device(p)
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "raytracer_screen.txt")
+        gpu_ctx.write_txt(p, path, run_time_s=0.25)
+        txt = open(path, "rb").read()
+    body = txt[txt.index(b"("):]
+    assert len(body) == g["pixel_bytes"]
+    assert pixel_md5(txt) == g["pixel_md5"]
+    head = txt[:txt.index(b"(")].decode().splitlines()
+    assert head[0] == "OSX Awesome Picture" and head[1] == f"Horizontal_Resolution:{g['W']}."
+    assert head[7] == "Run_Time:0.250000." and len(head) == 10
+
+
+# ---- the writer on arbitrary floats ------------------------------------------------------------------
+
+def test_writer_known_answers(gpu_ctx):
+    """main_test()'s gradient (RayTracer.cpp:1412-1444) and hand-picked values through the GPU
+    formatter vs glibc's "%f" (oracle) and Python's correctly rounded '%f'."""
+    w, h = 500, 504
+    i = np.arange(w, dtype=np.float32)[:, None] / np.float32(w)
+    j = np.arange(h, dtype=np.float32)[None, :] / np.float32(h)
+    px = np.stack([np.broadcast_to(i, (w, h)), np.broadcast_to(j, (w, h)), np.full((w, h), .5, np.float32)], -1)
+    got = gpu_ctx.format_pixels(px)
+    assert got == O.format_txt(px)
+    assert got.startswith(b"(0.000000, 0.000000, 0.500000)\n(0.000000, 0.001984, 0.500000)\n")
+    assert len(got) == w * h * 31
+    special = np.array([
+        [0.0, 1.0, 9.999999], [9.9999995, 0.0000005, 0.0000015], [0.0000025, 0.5, 0.125],
+        [1e-7, 4.9999997e-7, 5.0000003e-7], [1e-45, 1.17549435e-38, 2.5e-7],
+        [10.0, 123456.789, 16777216.0], [-0.0, -1.5, -0.0000004], [3.4028235e38, 1e20, 65535.0],
+        [np.inf, -np.inf, np.nan], [2.684511, 4.26, 0.75],
+    ], dtype=np.float32)
+    got = gpu_ctx.format_pixels(special)
+    assert got == O.format_txt(special)
+    lines = got.decode().splitlines()
+    for row, line in zip(special, lines):
+        if np.isfinite(row).all():
+            assert line == "(%f, %f, %f)" % tuple(float(v) for v in row)
+    assert lines[8] == "(inf, -inf, nan)"
+
+
+def test_writer_random_floats_fixed_and_general_paths(gpu_ctx):
+    rng = np.random.default_rng(1234)
+    # fixed path: all in [0, 10)
+    a = rng.random((50000, 3), dtype=np.float32) * np.float32(9.99)
+    a[::7] *= np.float32(1e-4)
+    assert gpu_ctx.format_pixels(a) == O.format_txt(a)
+    # exact ties of the 6th decimal: k + 0.5 micro-units that are representable
+    ties = (np.arange(1, 3001, dtype=np.float64) * 2 + 1) * 2.0 ** -21   # odd / 2^21
+    t32 = ties.astype(np.float32).reshape(-1, 3)
+    assert gpu_ctx.format_pixels(t32) == O.format_txt(t32)
+    # general path: random bit patterns (any exponent, sign, subnormals), no NaN payload issues
+    raw = rng.integers(0, 2 ** 32, size=(30000, 3), dtype=np.uint64).astype(np.uint32)
+    b = raw.view(np.float32)
+    b = np.where(np.isnan(b), np.float32(1.0), b)
+    got = gpu_ctx.format_pixels(b)
+    assert got == O.format_txt(b)
+    # mixed: mostly fixed with a few long lines
+    c = a.copy()
+    c[123, 1] = 10.5
+    c[40000, 0] = -3.0
+    assert gpu_ctx.format_pixels(c) == O.format_txt(c)
+
+
+# ---- properties at the BASELINE sizes -------------------------------------------------------------------
+
+def sampled_columns_match(ctx, scene_name, w, h, d, stride):
+    scene, cam = make_scene(scene_name)
+    ctx.upload(scene, cam)
+    p = api.default_params(w, h, d)
+    img, stats = ctx.render(p)
+    want, _ = O.render(scene.flatten(), cam.export(), p, 0, w, stride)
+    assert_bit_identical(img[0:w:stride], want, f"{scene_name} {w}x{h} sampled columns")
+    return img, stats, p
+
+
+def test_1080p_depth5_sampled_parity_and_band_stitching(gpu_ctx):
+    """configs[1]: every 16th column against the oracle; then the same image rendered as 1, 3 and
+    8 bands must be the same bits (the result of a pixel does not depend on the partition)."""
+    img, stats, p = sampled_columns_match(gpu_ctx, "default", 1920, 1080, 5, 16)
+    for n in (3, 8):
+        parts = []
+        rays = 0
+        for x0, x1 in column_bands(1920, n):
+            band, st = gpu_ctx.render(p, x0, x1)
+            parts.append(band)
+            rays += st.rays
+        assert np.array_equal(bits(np.concatenate(parts, 0)), bits(img))
+        assert rays == stats.rays
+    again, st2 = gpu_ctx.render(p)
+    assert np.array_equal(bits(again), bits(img)) and st2.rays == stats.rays     # idempotent
+
+
+def test_4k_depth50_sampled_parity_and_txt_round_trip(gpu_ctx):
+    """configs[2] on one GPU: sampled columns vs oracle; .txt lines parse back to the floats
+    (6 decimals) and every line is 31 bytes."""
+    img, stats, p = sampled_columns_match(gpu_ctx, "default", 3840, 2160, 50, 128)
+    assert stats.rays_primary == 3840 * 2160
+    n = gpu_ctx.txt_size()
+    assert n == 3840 * 2160 * 31
+    txt = gpu_ctx.format_txt()
+    assert txt[30:31] == b"\n" and txt[-1:] == b"\n"
+    sub = txt[: 31 * 2160 * 4]
+    vals = parse_txt(sub).reshape(4, 2160, 3)
+    assert np.abs(vals - img[:4].astype(np.float64)).max() <= 0.5e-6 + 1e-12
+
+
+def test_synth1024_4k_sampled_parity(gpu_ctx):
+    """configs[3]: 1027 objects at 3840x2160, every 256th column against the oracle."""
+    sampled_columns_match(gpu_ctx, "synth1024", 3840, 2160, 50, 256)
+
+
+def test_synth256_8k_sampled_parity(gpu_ctx):
+    """configs[4]: 259 objects at 7680x4320 depth 10, every 512th column against the oracle."""
+    img, stats, p = sampled_columns_match(gpu_ctx, "synth256", 7680, 4320, 10, 512)
+    assert img.shape == (7680, 4320, 3) and np.isfinite(img).all() and img.min() >= 0
+
+
+# ---- error behaviour of the boundary -------------------------------------------------------------------
+
+def test_error_codes(gpu_ctx):
+    fresh = api.Context([0])
+    p = api.default_params(8, 8, 2)
+    with pytest.raises(api.TcrtError) as e:
+        fresh.render(p)
+    assert e.value.code == _ffi.TCRT_ERR_NO_SCENE
+    scene, cam = make_scene("default")
+    fresh.upload(scene, cam)
+    with pytest.raises(api.TcrtError) as e:
+        fresh.txt_size()
+    assert e.value.code == _ffi.TCRT_ERR_NO_FRAME
+    for bad in (api.default_params(0, 8, 2), api.default_params(8, -1, 2), api.default_params(8, 8, -1)):
+        with pytest.raises(api.TcrtError) as e:
+            fresh.render_device(bad, 0, 1)
+        assert e.value.code == _ffi.TCRT_ERR_INVALID
+    with pytest.raises(api.TcrtError) as e:
+        fresh.render_device(api.default_params(8, 8, 255))
+    assert e.value.code == _ffi.TCRT_ERR_UNSUPPORTED
+    with pytest.raises(api.TcrtError) as e:
+        fresh.render_device(p, 3, 3)
+    assert e.value.code == _ffi.TCRT_ERR_INVALID
+    fresh.render_device(p, 2, 6)
+    with pytest.raises(api.TcrtError) as e:
+        fresh.write_txt(p, "/tmp/should_not_exist.txt")       # band, not the whole image
+    assert e.value.code == _ffi.TCRT_ERR_INVALID
+    fresh.render_device(p)
+    with pytest.raises(api.TcrtError) as e:
+        fresh.write_txt(p, "/nonexistent_dir/x/raytracer_screen.txt")
+    assert e.value.code == _ffi.TCRT_ERR_IO
+    with pytest.raises(api.TcrtError) as e:
+        api.Context([99])
+    assert e.value.code == _ffi.TCRT_ERR_NO_DEVICE
+    fresh.close()
+
+
+def test_multi_device_context_if_available(gpu_ctx):
+    """In-process band split over every visible GPU: same bits as one GPU."""
+    n = api.device_count()
+    if n < 2:
+        pytest.skip("one GPU visible")
+    scene, cam = make_scene("default")
+    p = api.default_params(640, 360, 8)
+    gpu_ctx.upload(scene, cam)
+    one, st1 = gpu_ctx.render(p)
+    multi = api.Context(list(range(n)))
+    multi.upload(scene, cam)
+    img, st = multi.render(p)
+    assert st.n_devices == n and st.bands == column_bands(640, n)
+    assert np.array_equal(bits(img), bits(one)) and st.rays == st1.rays
+    multi.render_device(p)
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "a.txt")
+        multi.write_txt(p, path)
+        gpu_ctx.render_device(p)
+        gpu_ctx.write_txt(p, os.path.join(td, "b.txt"))
+        assert open(path, "rb").read() == open(os.path.join(td, "b.txt"), "rb").read()
+    multi.close()

@@ -1,0 +1,260 @@
+"""CPU tests: the host construction API (include/CelioRayTracer.hpp, tcrt_host.h) and the
+C-ABI surface of libtcrt.so.  No compute calls: there is no GPU here and no CPU fallback."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle_py as O
+from tilecoderaytracer_b200 import _ffi, api
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+f32 = np.float32
+
+
+def arr(ptr, n):
+    return np.ctypeslib.as_array(ptr, shape=(n,)).copy()
+
+
+# ---- ABI surface -----------------------------------------------------------------------------
+
+def declared_symbols():
+    names = set()
+    for h in ("tcrt.h", "tcrt_host.h"):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b(tcrt_\w+)\s*\(", src))
+    return names
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _ffi.load()
+    decl = declared_symbols()
+    assert len(decl) >= 40
+    for name in sorted(decl):
+        assert hasattr(lib, name), f"{name} declared in include/*.h but not exported by libtcrt.so"
+    # and the Python binding table covers exactly the declared set
+    assert set(_ffi.SIGNATURES) == decl
+    out = subprocess.run(["nm", "-D", "--defined-only", _ffi.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (tcrt_\w+)", out))
+    assert decl <= exported
+
+
+def test_library_is_sm100a_only_and_has_no_oracle_dependency():
+    out = subprocess.run(["cuobjdump", "-lelf", _ffi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    assert not re.search(r"sm_(?!100a)\d+", out), out
+    ldd = subprocess.run(["ldd", _ffi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "liboracle" not in ldd
+    strings = subprocess.run(["strings", _ffi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "tcrt_oracle_render" not in strings
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    lib = _ffi.load()
+    n = lib.tcrt_device_count()
+    if n > 0:
+        pytest.skip("a GPU is visible here")
+    assert n in (_ffi.TCRT_ERR_NO_DEVICE, 0)
+    h = C.c_void_p()
+    rc = lib.tcrt_create(C.byref(h), None, 1)
+    assert rc == _ffi.TCRT_ERR_NO_DEVICE and not h.value
+    assert b"CUDA" in lib.tcrt_last_error(None) or b"device" in lib.tcrt_last_error(None)
+    with pytest.raises(api.TcrtError):
+        api.Context([0])
+
+
+def test_abi_version_and_default_params():
+    lib = _ffi.load()
+    assert lib.tcrt_abi_version() == 1
+    p = api.default_params()
+    # rt_project_parameters.h:65-66,73-74, RayTracer.h:52
+    assert (p.width, p.height, p.max_depth, p.shadows_on, p.reflections_on) == (500, 504, 50, 1, 1)
+    assert list(p.null_color) == [0.75, 0.75, 0.75] and p.far_dist == 65535.0
+
+
+def test_txt_header_matches_reference_file(golden):
+    """init_log + the three tags of printPixelsToLog, against the as-is program's own file."""
+    want = golden["asis"]["rt_asis"]["header_lines"]
+    rt = float(want[7].split(":")[1].rstrip("."))
+    got = api.txt_header(api.default_params(), rt).decode().splitlines()
+    assert got[:7] == want[:7]
+    assert got[7] == want[7]                       # Run_Time:%f.
+    assert got[8].startswith("us/pixel:") and got[9] == want[9]
+    assert abs(float(got[8].split(":")[1].rstrip(".")) - rt * 1e6 / (500 * 504)) < 1e-5
+    big = api.txt_header(api.default_params(7680, 4320, 10), 0.0).decode().splitlines()
+    assert big[1] == "Horizontal_Resolution:7680." and big[2] == "Vertical_Resolution:4320."
+
+
+# ---- camera ------------------------------------------------------------------------------------
+
+def test_camera_default_pose_and_eye_rays():
+    cam = api.Camera()
+    c = cam.export()
+    # Camera.cpp:22-38: horizontal ∝ (.1,-.08,0), vertical = horizontal x outward, eye one unit behind
+    h = np.array(c.horizontal[:], f32)
+    v = np.array(c.vertical[:], f32)
+    hx = f32(.1) / np.sqrt(f32(.1) * f32(.1) + f32(-.08) * f32(-.08) + f32(0), dtype=f32)
+    assert h[0] == f32(hx) and h[2] == 0
+    assert abs(float(np.dot(h, v))) < 1e-6 and abs(float(np.linalg.norm(v)) - 1) < 1e-6
+    assert list(c.screen_origin) == [-4.0, -4.0, 1.5]
+    assert (c.screen_width, c.screen_height, c.screen_halfwidth, c.screen_halfheight) == (1, 1, .5, .5)
+    eye = np.array(c.eye[:], f32)
+    assert abs(float(np.linalg.norm(eye - np.array([-4, -4, 1.5], f32))) - 1) < 1e-6
+    # createEyeRay (host) == primary-ray generation of the oracle, bit for bit
+    p = api.default_params(37, 23, 5)
+    for x, z in [(0, 0), (36, 22), (17, 5), (1, 21)]:
+        o1, d1 = cam.createEyeRay(f32(x) / f32(37), f32(z) / f32(23))
+        o2, d2 = O.primary_ray(c, p, x, z)
+        assert np.array_equal(o1.view(np.uint32), o2.view(np.uint32))
+        assert np.array_equal(d1.view(np.uint32), d2.view(np.uint32))
+        assert abs(float(np.linalg.norm(d1)) - 1) < 1e-6
+
+
+def test_camera_two_mirrors_pose():
+    cam = api.Camera()
+    cam.setSceneTwoMirrors()
+    c = cam.export()
+    assert list(c.screen_origin) == [0, 0, 2.5]
+    assert list(c.horizontal) == [1, 0, 0] and list(c.vertical) == [0, 0, 1]
+    assert list(c.eye) == [0, -1, 2.5]
+
+
+# ---- scenes ---------------------------------------------------------------------------------------
+
+def test_default_scene_object_list():
+    """SURVEY appendix A / Scene.cpp:209-387."""
+    s = api.Scene().initialize()
+    assert s.getObjectCount() == 32
+    f = s.flatten()
+    assert (f.n_spheres, f.n_inf_planes, f.n_fin_planes, f.n_lights, f.n_textures) == (7, 1, 24, 2, 1)
+    assert arr(f.sphere_obj, 7).tolist() == [0, 1, 2, 3, 4, 5, 6]
+    assert arr(f.inf_obj, 1).tolist() == [7]
+    assert arr(f.fin_obj, 24).tolist() == list(range(8, 32))
+    assert arr(f.light_obj, 2).tolist() == [0, 1]
+    sg = arr(f.sphere_geom, 28).reshape(7, 4)
+    assert sg[0].tolist() == [f32(6.99), f32(6.99), 5.5, f32(f32(.15) * f32(.15))]
+    assert sg[2].tolist() == [0, 0, 2, 1] and sg[5].tolist() == [0, 3, 1, 1] and sg[4][0] == -2.5
+    surf = arr(f.obj_surface, 128).reshape(32, 4)
+    mat = arr(f.obj_material, 128).reshape(32, 4)
+    info = arr(f.obj_info, 128).reshape(32, 4)
+    assert mat[0][2] == 0.75 and mat[1][2] == 1.0 and info[0][2] == 1 and info[2][2] == 0
+    assert surf[2].tolist() == [1, 0, 0, 1] and mat[2][1] == 1.0          # red mirror ball
+    assert surf[5].tolist() == [1, 1, 1, 0] and mat[5][1] == 1.0          # pure mirror, diffuse 0
+    assert mat[4][0] == 0.5                                               # specular .5
+    assert surf[7].tolist() == [0, 1, 0, 0.5] and mat[7][1] == 0.5 and info[7][3] == 0   # checker ground
+    assert arr(f.textures, 8).tolist() == [1, 1, 1, 3, 0, 0, 0, 3]
+    assert surf[8].tolist() == [f32(.2), f32(.2), 0, 1]                   # pedestal
+    assert mat[14][0] == f32(.2) and surf[20][0] == f32(.33) and mat[20][0] == 0
+    assert surf[26][0] == f32(2 / 3.) and mat[26][1] == 0.5 and mat[26][0] == 0.5
+
+
+def test_make_scene_box_faces():
+    """Scene.cpp:392-416: corners and the (origin, vertical corner, horizontal corner) face order."""
+    s = api.Scene()
+    faces = s.makeSceneBox((-7, -7, -1), (14, 14, 7))
+    assert [o.index for o in faces] == list(range(6))
+    f = s.flatten()
+    g = arr(f.fin_geom, 6 * 16).reshape(6, 4, 4)
+    org = arr(f.obj_origin, 24).reshape(6, 4)
+    # face 0 = (c0, c3, c2): origin c0, vertical along +z (7), horizontal along +y (14)
+    assert g[0][3][:3].tolist() == [-7, -7, -1]
+    assert g[0][1].tolist() == [0, 1, 0, 14] and g[0][2].tolist() == [0, 0, 1, 7]
+    assert g[0][0][:3].tolist() == [1, 0, 0]            # normal = horizontal x vertical
+    assert g[0][0][3] == -7.0                           # -distance_to_origin = origin . normal
+    # SceneObject origin moves to the far corner (SceneFinitePlane.cpp:74-79)
+    assert org[0][:3].tolist() == [-7, 7, 6]
+    # face 3 = (c7, c4, c6): origin c7
+    assert g[3][3][:3].tolist() == [7, 7, 6]
+    nrm = arr(f.obj_normals, 48).reshape(6, 2, 4)
+    assert np.allclose(nrm[:, 0, :3], -nrm[:, 1, :3])
+
+
+def test_finite_plane_axes_ctor_and_infinite_plane():
+    s = api.Scene()
+    s.addFinitePlaneAxes((-1.75, 7, 0), (0, -1, 0), (1, 0, 0), 5, 3.5)
+    s.addInfinitePlane((0, 0, 0), (0, 0, 2), (3, 0, 0))
+    f = s.flatten()
+    g = arr(f.fin_geom, 16).reshape(4, 4)
+    assert g[0].tolist() == [0, -1, 0, -7]       # normal, -dto = o.n = -7
+    assert g[1].tolist() == [1, 0, 0, 3.5] and g[2][3] == 5
+    assert g[2][:3].tolist() == [0, 0, 1]        # vertical = normal x horizontal
+    ig = arr(f.inf_geom, 16).reshape(4, 4)
+    assert ig[0].tolist() == [0, 0, 1, 0] and ig[1][:3].tolist() == [1, 0, 0] and ig[2][:3].tolist() == [0, 1, 0]
+    nrm = arr(f.obj_normals, 16).reshape(2, 2, 4)
+    assert nrm[1][1][:3].tolist() == [0, 0, -1]
+    # the reference negates with 0 - c (vector3d.h:113): the zero components stay +0
+    assert not np.signbit(nrm[1][1][0]) and not np.signbit(nrm[1][1][1])
+
+
+def test_material_defaults_and_setters():
+    s = api.Scene()
+    o = s.addSphere((1, 2, 3), 2.0)
+    f = s.flatten()
+    # ObjMaterial.h:13-21; SceneObject(origin) ctor leaves diffuse at 1
+    assert arr(f.obj_surface, 4).tolist() == [1, 1, 1, 1] and arr(f.obj_material, 4).tolist() == [1, 0, 1, 0]
+    o.setColor(.25, .5, .75).setDiffuseFactor(.1).setSpecularFactor(.2).setReflectiveFactor(.3)
+    o.setAsLightSource(.6)
+    o.setCheckerBoard((1, 0, 0), (0, 0, 1), 2.5, 1.5)
+    f = s.flatten()
+    assert arr(f.obj_surface, 4).tolist() == [.25, .5, .75, f32(.1)]
+    assert arr(f.obj_material, 4).tolist() == [f32(.2), f32(.3), f32(.6), 0]
+    assert arr(f.obj_info, 4).tolist() == [0, 0, 1, 0] and f.n_lights == 1 and f.n_textures == 1
+    assert arr(f.textures, 8).tolist() == [1, 0, 0, 2.5, 0, 0, 1, 1.5]
+    assert arr(f.sphere_geom, 4).tolist() == [1, 2, 3, 4]
+
+
+def test_add_object_refuses_at_capacity(capfd):
+    """Scene::addObject: `object_count+1 >= MAX_OBJECT_COUNT` -> message, no add (Scene.cpp:470-479)."""
+    s = api.Scene()
+    for i in range(3999):
+        s.addSphere((i, 0, 0), 1)
+    assert s.getObjectCount() == 3999
+    with pytest.raises(api.TcrtError):
+        s.addSphere((0, 0, 0), 1)
+    assert s.getObjectCount() == 3999
+    assert "Added too many objects" in capfd.readouterr().out
+
+
+def test_two_mirrors_and_synthetic_counts():
+    cam = api.Camera()
+    s = api.Scene().initializeTwoMirrors(cam)
+    assert s.getObjectCount() == 3920            # Scene.cpp:131 "3920 we need this number of objects"
+    f = s.flatten()
+    assert (f.n_spheres, f.n_inf_planes, f.n_fin_planes, f.n_lights) == (3915, 1, 4, 1)
+    assert list(cam.export().eye) == [0, -1, 2.5]
+    assert api.Scene().build("synth1024").getObjectCount() == 1027
+    assert api.Scene().build("synth256").getObjectCount() == 259
+    with pytest.raises(api.TcrtError):
+        api.Scene().build("no_such_scene")
+
+
+def test_finite_plane_threshold_is_a_float_compare():
+    """`t < 1E-5` is a double compare in the reference (SceneFinitePlane.cpp:102); the kernels
+    use t <= 9.99999974738e-06f.  Equivalent for every float around the threshold."""
+    thr = f32(9.99999974738e-06)
+    assert float(thr) < 1e-5 < float(np.nextafter(thr, f32(1)))
+    t = thr
+    for _ in range(2000):
+        t = np.nextafter(t, f32(0))
+    for _ in range(4000):
+        assert (float(t) < 1e-5) == bool(t <= thr)
+        t = np.nextafter(t, f32(1))
+    for special in (f32(0), f32(-0.0), f32(-1), f32(np.inf), f32(np.nan)):
+        assert (float(special) < 1e-5) == bool(special <= thr)
+
+
+def test_partition_tiles_the_image():
+    from tilecoderaytracer_b200.partition import column_band, column_bands
+
+    for w in (1, 7, 500, 1920, 3840, 7680):
+        for n in (1, 2, 3, 4, 8):
+            bands = column_bands(w, n)
+            assert bands[0][0] == 0 and bands[-1][1] == w
+            assert all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
+            assert max(b - a for a, b in bands) - min(b - a for a, b in bands) <= 1
+    with pytest.raises(ValueError):
+        column_band(10, 2, 2)

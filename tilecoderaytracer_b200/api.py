@@ -265,6 +265,13 @@ class Context:
     def flush_l2(self) -> None:
         self._ck(self._lib.tcrt_flush_l2(self._h))
 
+    def fp32_peak(self) -> dict:
+        """Measured FP32-pipe issue peak of device slot 0 (1e12 lane-instructions/s)."""
+        u, f = C.c_double(), C.c_double()
+        ms = (C.c_double * 2)()
+        self._ck(self._lib.tcrt_fp32_peak(self._h, C.byref(u), C.byref(f), ms))
+        return {"unfused_tera_inst": u.value, "fma_tera_inst": f.value, "ms": [ms[0], ms[1]]}
+
     def txt_size(self) -> int:
         n = C.c_size_t()
         self._ck(self._lib.tcrt_txt_size(self._h, C.byref(n)))
@@ -280,6 +287,17 @@ class Context:
         got = C.c_size_t()
         self._ck(self._lib.tcrt_format_txt(self._h, out.ctypes.data_as(C.c_void_p), out.nbytes, C.byref(got)))
         return out[: got.value]
+
+    def format_pixels(self, rgb: np.ndarray) -> bytes:
+        """The writer's pixel lines for arbitrary float32 pixels (n,3)."""
+        rgb = np.ascontiguousarray(rgb, dtype=np.float32).reshape(-1, 3)
+        n = rgb.shape[0]
+        cap = n * 148 + 16
+        buf = np.empty(cap, dtype=np.uint8)
+        got = C.c_size_t()
+        self._ck(self._lib.tcrt_format_pixels(self._h, rgb.ctypes.data_as(C.c_void_p), n,
+                                              buf.ctypes.data_as(C.c_void_p), cap, C.byref(got)))
+        return buf[: got.value].tobytes()
 
     def write_txt(self, params: TcrtParams, path: str, run_time_s: float = 0.0) -> None:
         self._ck(self._lib.tcrt_write_txt(self._h, C.byref(params), path.encode(), run_time_s))

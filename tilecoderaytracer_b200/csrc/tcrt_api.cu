@@ -469,6 +469,34 @@ int tcrt_flush_l2(tcrt_ctx* ctx) {
     return TCRT_OK;
 }
 
+int tcrt_fp32_peak(tcrt_ctx* ctx, double* unfused, double* fma, double* ms_each) {
+    if (!ctx || !unfused || !fma) return fail(ctx, TCRT_ERR_INVALID, "null argument");
+    DeviceState& d = ctx->devs[0];
+    CK(ctx, cudaSetDevice(d.dev));
+    const int grid = d.sm_count * 8;      // 8 CTAs x 8 warps = the full 64 warps per SM
+    const int iters = 1 << 16;
+    double res[2] = {0, 0}, ms_out[2] = {0, 0};
+    for (int mode = 0; mode < 2; mode++) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; rep++) {   // first rep warms up
+            CK(ctx, cudaEventRecord(d.ev_k0, d.stream));
+            CK(ctx, tcrt_launch_fp32_peak(mode == 1, reinterpret_cast<float*>(d.flag), grid, iters, d.stream));
+            CK(ctx, cudaEventRecord(d.ev_k1, d.stream));
+            CK(ctx, cudaStreamSynchronize(d.stream));
+            float ms = 0.f;
+            CK(ctx, cudaEventElapsedTime(&ms, d.ev_k0, d.ev_k1));
+            if (rep > 0 && ms < best) best = ms;
+        }
+        const double lane_inst = (double)grid * 256.0 * (double)iters * 8.0 * (mode == 1 ? 1.0 : 2.0);
+        res[mode] = lane_inst / (best * 1e-3) / 1e12;
+        ms_out[mode] = best;
+    }
+    *unfused = res[0];
+    *fma = res[1];
+    if (ms_each) { ms_each[0] = ms_out[0]; ms_each[1] = ms_out[1]; }
+    return TCRT_OK;
+}
+
 // ---- .txt writer -----------------------------------------------------------------------------------
 // Decide fixed/general per device and size the output.
 static int prepare_txt(tcrt_ctx* ctx) {
@@ -545,6 +573,34 @@ int tcrt_format_txt(tcrt_ctx* ctx, char* host_text, size_t cap, size_t* n_bytes)
     }
     if (n_bytes) *n_bytes = total;
     return TCRT_OK;
+}
+
+int tcrt_format_pixels(tcrt_ctx* ctx, const float* host_rgb, size_t n_pixels, char* host_text, size_t cap,
+                       size_t* n_bytes) {
+    if (!ctx || (!host_rgb && n_pixels) || !host_text || !n_bytes) return fail(ctx, TCRT_ERR_INVALID, "null argument");
+    *n_bytes = 0;
+    if (n_pixels == 0) return TCRT_OK;
+    if (n_pixels > (size_t)0x7fffffff / 3) return fail(ctx, TCRT_ERR_INVALID, "too many pixels");
+    DeviceState& d = ctx->devs[0];
+    CK(ctx, cudaSetDevice(d.dev));
+    // the frame buffer doubles as the staging area: the last render is gone afterwards
+    ctx->has_frame = false;
+    ctx->txt_prepared = false;
+    int rc = ensure(ctx, d.frame, d.frame_cap, n_pixels * 3);
+    if (rc) return rc;
+    CK(ctx, cudaMemcpyAsync(d.frame, host_rgb, n_pixels * 3 * sizeof(float), cudaMemcpyHostToDevice, d.stream));
+    for (auto& o : ctx->devs) o.x0 = o.x1 = 0;
+    d.x0 = 0;
+    d.x1 = 1;                 // one "column" of n_pixels rows
+    d.height = (int)n_pixels;
+    ctx->has_frame = true;
+    ctx->frame_x0 = 0;
+    ctx->frame_x1 = 1;
+    ctx->frame_h = (int)n_pixels;
+    rc = tcrt_format_txt(ctx, host_text, cap, n_bytes);
+    ctx->has_frame = false;
+    ctx->txt_prepared = false;
+    return rc;
 }
 
 int tcrt_txt_header(const tcrt_params* p, double run_time_s, char* buf, size_t cap) {

@@ -274,3 +274,30 @@ cudaError_t tcrt_launch_l2_flush(void* scratch, size_t bytes, cudaStream_t strea
     l2_flush_kernel<<<148 * 4, 256, 0, stream>>>(reinterpret_cast<uint4*>(scratch), bytes / 16);
     return cudaGetLastError();
 }
+
+// ---- FP32 pipe microbenchmark (roofline denominator) -------------------------------------------
+namespace {
+template <bool FMA>
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, float m, float c) {
+    float a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = (float)(threadIdx.x + k) * 1e-3f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (FMA) a[k] = __fmaf_rn(a[k], m, c);
+            else a[k] = __fadd_rn(__fmul_rn(a[k], m), c);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += a[k];
+    if (s == 123.456f) out[0] = s;   // keep the chains alive
+}
+}  // namespace
+
+cudaError_t tcrt_launch_fp32_peak(bool fma, float* scratch, int grid, int iters, cudaStream_t stream) {
+    if (fma) fp32_peak_kernel<true><<<grid, 256, 0, stream>>>(scratch, iters, 0.999f, 1e-3f);
+    else fp32_peak_kernel<false><<<grid, 256, 0, stream>>>(scratch, iters, 0.999f, 1e-3f);
+    return cudaGetLastError();
+}

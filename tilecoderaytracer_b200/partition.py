@@ -1,0 +1,20 @@
+"""Column-band partition of an image over ranks / devices.
+
+The reference's static scheme (strategy 1, RayTracer.cpp:904-906) gives rank r the rows
+[r*dz, r*dz+dz) with dz = H / CORE_NUM.  Here the band axis is x, because the pixel array and
+the .txt are x-major (RayTracer.h:44, RayTracer.cpp:1589-1590): a band of columns is one
+contiguous slice of both, so bands are copied back and concatenated without a transpose and
+without any inter-GPU exchange.  libtcrt.so uses the same formula for a multi-device ctx.
+"""
+from __future__ import annotations
+
+
+def column_band(width: int, rank: int, world: int) -> tuple[int, int]:
+    """Columns [x0, x1) of rank `rank` out of `world`; bands tile [0, width) exactly."""
+    if world < 1 or not (0 <= rank < world) or width < 0:
+        raise ValueError("bad partition arguments")
+    return (width * rank) // world, (width * (rank + 1)) // world
+
+
+def column_bands(width: int, world: int) -> list[tuple[int, int]]:
+    return [column_band(width, r, world) for r in range(world)]
