@@ -332,3 +332,30 @@ def test_multi_device_context_if_available(gpu_ctx):
         gpu_ctx.write_txt(p, os.path.join(td, "b.txt"))
         assert open(path, "rb").read() == open(os.path.join(td, "b.txt"), "rb").read()
     multi.close()
+
+
+def test_cpp_host_program_is_a_drop_in(golden, tmp_path):
+    """examples/raytrace_main.cpp: the reference's main()/raytrace_main() flow written against the
+    drop-in C++ headers, linked with libtcrt.so.  Its raytracer_screen.txt must carry the same pixel
+    lines as the reference program's (rt_asis) and the same header layout."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "tilecoderaytracer_b200")
+    exe = tmp_path / "raytrace_main"
+    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "examples", "raytrace_main.cpp"), "-L", libdir, "-ltcrt",
+                    f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    txt = (tmp_path / "raytracer_screen.txt").read_bytes()
+    assert pixel_md5(txt) == golden["asis"]["rt_asis"]["pixel_md5"]
+    head = txt[:txt.index(b"(")].decode().splitlines()
+    want = golden["asis"]["rt_asis"]["header_lines"]
+    strip = lambda ls: [l for l in ls if not l.startswith(("Run_Time", "us/pixel"))]
+    assert strip(head) == strip(want) and len(head) == len(want)
+    # SCENE 2 through the same program
+    r = subprocess.run([str(exe), "2"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    txt = (tmp_path / "raytracer_screen.txt").read_bytes()
+    assert pixel_md5(txt) == golden["md5"]["two_mirrors_500x504_d50"]["pixel_md5"]
