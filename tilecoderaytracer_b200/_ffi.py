@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtcrt.so")
+# TCRT_LIB: developer override used to A/B kernel variants (tools/quick_perf.py); the product path is the default
+LIB_PATH = os.environ.get("TCRT_LIB") or os.path.join(_HERE, "libtcrt.so")
 
 TCRT_MAX_DEVICES = 16
 TCRT_OK = 0

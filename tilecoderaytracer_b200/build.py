@@ -33,7 +33,7 @@ NVCC_FLAGS = [
 CXX_FLAGS = ["-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-Wall"]
 INCLUDES = ["-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "scenes")]
 
-CUDA_SOURCES = ["tcrt_render.cu", "tcrt_format.cu", "tcrt_api.cu"]
+CUDA_SOURCES = ["tcrt_render.cu", "tcrt_format.cu", "tcrt_api.cu", "tcrt_bvh.cpp"]
 HOST_SOURCES = ["host_scene.cpp", "host_capi.cpp"]
 
 
@@ -60,16 +60,18 @@ def _deps() -> list[str]:
     return deps
 
 
-def build_lib(force: bool = False, verbose_ptxas: bool = False) -> str:
-    """Compile libtcrt.so for sm_100a (cross-compiles without a GPU)."""
-    if not force and not _stale(LIB_PATH, _deps()):
-        return LIB_PATH
-    objdir = os.path.join(PKG, "build")
+def build_lib(force: bool = False, verbose_ptxas: bool = False, defines: tuple = (), out: str | None = None) -> str:
+    """Compile libtcrt.so for sm_100a (cross-compiles without a GPU).  `defines`/`out` build a
+    developer variant (e.g. ("TCRT_MIN_BLOCKS=3",) -> libtcrt_mb3.so) for A/B timing."""
+    lib_path = out or LIB_PATH
+    if not force and not _stale(lib_path, _deps()):
+        return lib_path
+    objdir = os.path.join(PKG, "build", os.path.basename(lib_path))
     os.makedirs(objdir, exist_ok=True)
     objs = []
     for src in CUDA_SOURCES:
         obj = os.path.join(objdir, src + ".o")
-        cmd = [NVCC, *NVCC_FLAGS, *INCLUDES, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [NVCC, *NVCC_FLAGS, *INCLUDES, *[f"-D{d}" for d in defines], "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose_ptxas:
             cmd[1:1] = ["-Xptxas", "-v"]
         _run(cmd)
@@ -80,8 +82,8 @@ def build_lib(force: bool = False, verbose_ptxas: bool = False) -> str:
         objs.append(obj)
     # static cudart: the library has no run-time dependency beyond libcuda (the driver)
     _run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static",
-          *objs, "-o", LIB_PATH, "-lpthread"])
-    return LIB_PATH
+          *objs, "-o", lib_path, "-lpthread"])
+    return lib_path
 
 
 def build_oracle(force: bool = False) -> str:

@@ -5,6 +5,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <math.h>
+
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -111,6 +114,67 @@ void free_device(DeviceState& d) {
     if (d.stream) cudaStreamDestroy(d.stream);
     d = DeviceState{};
 }
+
+// ---- conservative boxes for the BVH (all maths in double, then widened) ---------------------------
+// A sphere hit point lies on the sphere; a finite-plane hit point P satisfies
+// 0 <= (P-po).h <= h_dist and 0 <= (P-po).v <= v_dist (SceneFinitePlane.cpp:116-122) on the plane
+// n.P = -dto.  h, v need not be orthogonal to each other or to n (three-corner ctor with skewed
+// corners, or the axes ctor with a slanted normal), so the accepted region is the parallelogram cut
+// out of the plane by the two slabs; its corners come from 2x2 solves in an in-plane basis.
+void sphere_box(const float* g, double margin, float* box) {
+    double r = sqrt(std::max(0.0, (double)g[3])) * (1.0 + 1e-6);
+    for (int k = 0; k < 3; k++) {
+        box[k] = (float)((double)g[k] - r - margin - 1e-6 * fabs((double)g[k]));
+        box[3 + k] = (float)((double)g[k] + r + margin + 1e-6 * fabs((double)g[k]));
+    }
+}
+
+void fin_box(const float* g, double margin, float* box) {
+    const double n[3] = {g[0], g[1], g[2]}, h[3] = {g[4], g[5], g[6]}, v[3] = {g[8], g[9], g[10]};
+    const double hd = g[7], vd = g[11], po[3] = {g[12], g[13], g[14]};
+    auto unbounded = [&]() {
+        for (int k = 0; k < 3; k++) { box[k] = -INFINITY; box[3 + k] = INFINITY; }
+    };
+    double nn = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    if (!(nn > 1e-12) || !std::isfinite(nn) || !std::isfinite(hd) || !std::isfinite(vd)) return unbounded();
+    double nu[3] = {n[0] / nn, n[1] / nn, n[2] / nn};
+    // in-plane orthonormal basis e1, e2
+    int m = fabs(nu[0]) < fabs(nu[1]) ? (fabs(nu[0]) < fabs(nu[2]) ? 0 : 2) : (fabs(nu[1]) < fabs(nu[2]) ? 1 : 2);
+    double a[3] = {0, 0, 0};
+    a[m] = 1.0;
+    double e1[3] = {nu[1] * a[2] - nu[2] * a[1], nu[2] * a[0] - nu[0] * a[2], nu[0] * a[1] - nu[1] * a[0]};
+    double l1 = sqrt(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]);
+    for (int k = 0; k < 3; k++) e1[k] /= l1;
+    double e2[3] = {nu[1] * e1[2] - nu[2] * e1[1], nu[2] * e1[0] - nu[0] * e1[2], nu[0] * e1[1] - nu[1] * e1[0]};
+    auto dot3 = [](const double* x, const double* y) { return x[0] * y[0] + x[1] * y[1] + x[2] * y[2]; };
+    // constraints on q = (u, w), P - po = u e1 + w e2 :  0 <= a1.q <= hd,  0 <= a2.q <= vd
+    double a1[2] = {dot3(h, e1), dot3(h, e2)}, a2[2] = {dot3(v, e1), dot3(v, e2)};
+    double det = a1[0] * a2[1] - a1[1] * a2[0];
+    double scale = sqrt((a1[0] * a1[0] + a1[1] * a1[1]) * (a2[0] * a2[0] + a2[1] * a2[1]));
+    if (!(fabs(det) > 1e-6 * scale) || !(scale > 0)) return unbounded();
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    const double slack = 1e-5;   // the slab tests themselves are evaluated in float
+    for (int ci = 0; ci < 4; ci++) {
+        double x = (ci & 1) ? hd * (1 + slack) + slack : -slack * (1 + fabs(hd));
+        double y = (ci & 2) ? vd * (1 + slack) + slack : -slack * (1 + fabs(vd));
+        double u = (x * a2[1] - a1[1] * y) / det, w = (a1[0] * y - a2[0] * x) / det;
+        for (int k = 0; k < 3; k++) {
+            double c = po[k] + u * e1[k] + w * e2[k];
+            lo[k] = std::min(lo[k], c);
+            hi[k] = std::max(hi[k], c);
+        }
+    }
+    for (int k = 0; k < 3; k++) {
+        double pad = margin + 1e-5 * (fabs(lo[k]) + fabs(hi[k]) + (hi[k] - lo[k]));
+        box[k] = (float)(lo[k] - pad);
+        box[3 + k] = (float)(hi[k] + pad);
+        if (!std::isfinite(box[k]) || !std::isfinite(box[3 + k])) { box[k] = -INFINITY; box[3 + k] = INFINITY; }
+    }
+}
+
+// below these counts a linear sweep over shared memory is faster than a traversal
+constexpr int kSphereBvhMin = 24;
+constexpr int kFinBvhMin = 64;
 
 bool valid_params(const tcrt_params* p) {
     return p && p->width > 0 && p->height > 0 && p->max_depth >= 0 &&
@@ -245,6 +309,85 @@ int tcrt_upload_scene(tcrt_ctx* ctx, const tcrt_scene* s, const tcrt_camera* cam
     order(s->fin_obj, s->n_fin_planes, pf, ds.n_fin_nl);
     order(s->inf_obj, s->n_inf_planes, pi, ds.n_inf_nl);
 
+    // BVHs over the non-light primitives of a type when there are many; the covered prefix of the
+    // type's array is re-ordered into leaf order.  `n_*_nl` keeps meaning "non-light" (the shadow
+    // sweep's range); `n_*_bvh` <= n_*_nl is the BVH-covered prefix, the rest is swept linearly.
+    std::vector<float4> bvh_s, bvh_f;
+    ds.bvh_sph_root = ds.bvh_fin_root = 0;
+    ds.n_sph_bvh = ds.n_fin_bvh = 0;
+    ds.bvh_cx = ds.bvh_cy = ds.bvh_cz = ds.bvh_r2 = ds.bvh_cmax = 0.f;
+    ds.bvh_rmin = 1.f;
+    {
+        double ext = 1.0;
+        for (int i = 0; i < s->n_spheres; i++)
+            for (int k = 0; k < 3; k++) ext = std::max(ext, fabs((double)s->sphere_geom[4 * i + k]));
+        for (int i = 0; i < s->n_fin_planes; i++)
+            for (int k = 0; k < 3; k++) ext = std::max(ext, fabs((double)s->fin_geom[16 * i + 12 + k]));
+        if (!std::isfinite(ext)) ext = 1e30;
+        const double margin = 1e-5 * ext;
+        std::vector<float> boxes_s, boxes_f;
+        std::vector<int> ord;
+        double blo[3] = {1e300, 1e300, 1e300}, bhi[3] = {-1e300, -1e300, -1e300};
+        auto grow = [&](const float* bx) {
+            for (int k = 0; k < 3; k++) {
+                if (std::isfinite(bx[k])) blo[k] = std::min(blo[k], (double)bx[k]);
+                if (std::isfinite(bx[3 + k])) bhi[k] = std::max(bhi[k], (double)bx[3 + k]);
+            }
+        };
+        if (ds.n_sph_nl >= kSphereBvhMin) {
+            // Tiny spheres would force a large per-ray fattening on everything (see `fatten`): the
+            // (at most 16) spheres below half the median radius stay in the linear part.
+            std::vector<float> rad(ds.n_sph_nl);
+            for (int k = 0; k < ds.n_sph_nl; k++) rad[k] = sqrtf(std::max(0.f, s->sphere_geom[4 * ps[k] + 3]));
+            std::vector<float> sorted(rad);
+            std::sort(sorted.begin(), sorted.end());
+            float r_cut = 0.5f * sorted[sorted.size() / 2];
+            if (sorted.size() > 16 && sorted[16] < r_cut) r_cut = sorted[16];   // never more than 16 outside
+            std::vector<int> in, out;
+            for (int k = 0; k < ds.n_sph_nl; k++) (rad[k] >= r_cut && rad[k] > 0.f ? in : out).push_back(ps[k]);
+            const int nb = (int)in.size();
+            boxes_s.resize(6 * (size_t)nb);
+            float rmin = INFINITY;
+            for (int k = 0; k < nb; k++) {
+                sphere_box(s->sphere_geom + 4 * in[k], margin, &boxes_s[6 * k]);
+                grow(&boxes_s[6 * k]);
+                rmin = std::min(rmin, sqrtf(s->sphere_geom[4 * in[k] + 3]));
+            }
+            ds.bvh_sph_root = tcrt_build_bvh(boxes_s, nb, ord, bvh_s);
+            std::vector<int> np;
+            for (int k = 0; k < nb; k++) np.push_back(in[ord[k]]);
+            np.insert(np.end(), out.begin(), out.end());
+            np.insert(np.end(), ps.begin() + ds.n_sph_nl, ps.end());
+            ps.swap(np);
+            ds.n_sph_bvh = nb;
+            ds.bvh_rmin = rmin * 0.999f;
+        }
+        if (ds.n_fin_nl >= kFinBvhMin) {
+            boxes_f.resize(6 * (size_t)ds.n_fin_nl);
+            for (int k = 0; k < ds.n_fin_nl; k++) {
+                fin_box(s->fin_geom + 16 * pf[k], margin, &boxes_f[6 * k]);
+                grow(&boxes_f[6 * k]);
+            }
+            ds.bvh_fin_root = tcrt_build_bvh(boxes_f, ds.n_fin_nl, ord, bvh_f);
+            std::vector<int> np(pf);
+            for (int k = 0; k < ds.n_fin_nl; k++) np[k] = pf[ord[k]];
+            pf.swap(np);
+            ds.n_fin_bvh = ds.n_fin_nl;
+        }
+        if (!bvh_s.empty() || !bvh_f.empty() || ds.n_sph_bvh || ds.n_fin_bvh) {
+            double c[3], r2 = 0.0, cmax = 0.0;
+            for (int k = 0; k < 3; k++) {
+                if (!(blo[k] <= bhi[k])) blo[k] = bhi[k] = 0.0;
+                c[k] = 0.5 * (blo[k] + bhi[k]);
+                r2 += 0.25 * (bhi[k] - blo[k]) * (bhi[k] - blo[k]);
+                cmax = std::max(cmax, std::max(fabs(blo[k]), fabs(bhi[k])));
+            }
+            ds.bvh_cx = (float)c[0]; ds.bvh_cy = (float)c[1]; ds.bvh_cz = (float)c[2];
+            ds.bvh_r2 = (float)(r2 * 1.001 + 1e-6);
+            ds.bvh_cmax = (float)(cmax * 1.001);
+        }
+    }
+
     ds.fin_off = ds.n_sph;
     ds.inf_off = ds.fin_off + 4 * ds.n_fin;
     ds.light_off = ds.inf_off + ds.n_inf;
@@ -260,7 +403,9 @@ int tcrt_upload_scene(tcrt_ctx* ctx, const tcrt_scene* s, const tcrt_camera* cam
     const size_t off_normals = off_material + n;
     const size_t off_frame = off_normals + 2 * (size_t)n;
     const size_t off_tex = off_frame + 3 * (size_t)ds.n_inf;
-    const size_t total_f4 = off_tex + 2 * (size_t)s->n_textures + 1;
+    const size_t off_bvh_s = off_tex + 2 * (size_t)s->n_textures;
+    const size_t off_bvh_f = off_bvh_s + bvh_s.size();
+    const size_t total_f4 = off_bvh_f + bvh_f.size() + 1;
     std::vector<float4> host(total_f4, make_float4(0.f, 0.f, 0.f, 0.f));
     auto f4 = [](const float* p) { return make_float4(p[0], p[1], p[2], p[3]); };
     int* idx = reinterpret_cast<int*>(&host[ds.idx_off]);
@@ -299,6 +444,8 @@ int tcrt_upload_scene(tcrt_ctx* ctx, const tcrt_scene* s, const tcrt_camera* cam
         host[off_tex + 2 * t] = f4(s->textures + 8 * t);
         host[off_tex + 2 * t + 1] = f4(s->textures + 8 * t + 4);
     }
+    std::copy(bvh_s.begin(), bvh_s.end(), host.begin() + off_bvh_s);
+    std::copy(bvh_f.begin(), bvh_f.end(), host.begin() + off_bvh_f);
 
     for (auto& d : ctx->devs) {
         CK(ctx, cudaSetDevice(d.dev));
@@ -314,6 +461,8 @@ int tcrt_upload_scene(tcrt_ctx* ctx, const tcrt_scene* s, const tcrt_camera* cam
         d.ds.inf_frame = d.scene_mem + off_frame;
         d.ds.textures = d.scene_mem + off_tex;
         d.ds.obj_info = nullptr;
+        d.ds.bvh_sph = bvh_s.empty() ? nullptr : d.scene_mem + off_bvh_s;
+        d.ds.bvh_fin = bvh_f.empty() ? nullptr : d.scene_mem + off_bvh_f;
     }
     ctx->cam = *cam;
     ctx->has_scene = true;

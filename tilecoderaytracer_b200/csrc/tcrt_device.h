@@ -27,6 +27,7 @@ struct DeviceScene {
     int blob_f4;               // size in float4 units (including the index tail, rounded up)
     int n_sph, n_fin, n_inf;
     int n_sph_nl, n_fin_nl, n_inf_nl;   // non-light prefix lengths
+    int n_sph_bvh, n_fin_bvh;           // BVH-covered prefix of the non-light prefix (0 = none)
     int n_lights;
     int fin_off, inf_off, light_off, idx_off;   // float4 offsets into the blob
     // winner-only, indexed by object index
@@ -36,7 +37,23 @@ struct DeviceScene {
     const int4* obj_info;        // type, slot (position in the permuted type array), is_light, texture id
     const float4* inf_frame;     // 3 per infinite plane slot: horizontal, vertical, origin
     const float4* textures;      // 2 per texture: (light rgb, width) (dark rgb, height)
+    // optional BVHs over the non-light spheres / finite planes (nullptr = linear sweep); the
+    // type's primitive array is then in leaf order.  Node layout: see tcrt_render.cu.
+    const float4* bvh_sph;
+    const float4* bvh_fin;
+    int bvh_sph_root, bvh_fin_root;   // encoded like a child reference
+    // per-ray fattening of the boxes (tcrt_render.cu `fatten`): bounding sphere (centre, radius^2)
+    // of everything inside the BVHs, smallest BVH sphere radius, largest |coordinate|
+    float bvh_cx, bvh_cy, bvh_cz, bvh_r2, bvh_rmin, bvh_cmax;
 };
+
+// host BVH builder (tcrt_bvh.cpp).  boxes: n x 6 floats (lo xyz, hi xyz), already inflated.
+// On return `order` is the leaf order (a permutation of 0..n-1), `nodes` 4 float4 per node,
+// and the function value is the encoded root reference.
+#ifdef __cplusplus
+#include <vector>
+int tcrt_build_bvh(const std::vector<float>& boxes, int n, std::vector<int>& order, std::vector<float4>& nodes);
+#endif
 
 struct RenderLaunch {
     DeviceScene scene;
