@@ -19,7 +19,7 @@
 // are also written with the reference's pixel-line format string (RayTracer.cpp:1601).
 //
 // usage: ref_render <scene> <W> <H> <max_depth> <x0> <x1> <out.f32|-> [--txt file] [--stride s]
-//   scene: default | two_mirrors | synth1024 | synth256 | random:<seed>:<n_objects>
+//   scene: default | two_mirrors | synth1024 | synth256 | random:<seed>:<n_objects> | boxes:<seed>:<n_boxes>
 //   --stride s : render only columns x0, x0+s, x0+2s, ... (bounded CPU samples for bench.py)
 
 int g_ref_max_depth = 50;   // replaces the literal of rt_project_parameters.h:73
@@ -81,6 +81,10 @@ int main(int argc, char** argv) {
         unsigned int seed = 0; int n = 0;
         if (sscanf(scene_name + 7, "%u:%d", &seed, &n) != 2) { fprintf(stderr, "bad random spec\n"); return 2; }
         tcrt_scenes::build_random(my_scene, seed, n);
+    } else if (!strncmp(scene_name, "boxes:", 6)) {
+        unsigned int seed = 0; int n = 0;
+        if (sscanf(scene_name + 6, "%u:%d", &seed, &n) != 2) { fprintf(stderr, "bad boxes spec\n"); return 2; }
+        tcrt_scenes::build_boxes(my_scene, seed, n);
     } else {
         fprintf(stderr, "unknown scene %s\n", scene_name);
         return 2;

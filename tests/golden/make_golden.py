@@ -53,6 +53,8 @@ FRAME_CONFIGS = [
     ("random_5_25_96x80_d3", "random:5:25", 96, 80, 3),
     ("random_7_120_96x80_d12", "random:7:120", 96, 80, 12),
     ("random_3_300_64x48_d20", "random:3:300", 64, 48, 20),
+    ("boxes_1_6_96x80_d8", "boxes:1:6", 96, 80, 8),          # axis-aligned boxes: the box-cluster path
+    ("boxes_3_14_96x80_d12", "boxes:3:14", 96, 80, 12),
 ]
 
 

@@ -64,6 +64,16 @@ def test_random_scenes_bit_exact(gpu_ctx, seed, n):
     check_counters(stats, cnt)
 
 
+@pytest.mark.parametrize("seed,n", [(1, 6), (2, 10), (3, 14), (4, 3), (5, 0), (6, 9), (7, 9), (8, 4)])
+def test_axis_aligned_box_scenes_bit_exact(gpu_ctx, seed, n):
+    """Fuzz of the box-cluster path: makeSceneBox boxes (stacked / abutting / duplicated: exact distance
+    ties on coplanar faces go to the lower object index), lone axis-aligned rectangles of every sign
+    combination, spheres and skewed planes in between, inside a closed room (up to 63 finite planes)."""
+    img, stats, want, cnt = gpu_and_oracle(gpu_ctx, f"boxes:{seed}:{n}", 128, 96, 12)
+    assert_bit_identical(img, want, f"boxes:{seed}:{n}")
+    check_counters(stats, cnt)
+
+
 def test_switches_shadows_reflections(gpu_ctx):
     for kw in ({"shadows": False}, {"reflections": False}, {"shadows": False, "reflections": False}):
         img, stats, want, cnt = gpu_and_oracle(gpu_ctx, "default", 120, 90, 7, **kw)

@@ -26,7 +26,7 @@ def oracle_frame(scene_name, w, h, depth, **kw):
 
 def test_oracle_matches_golden_frames(golden, golden_frames):
     """Bit-exact on every committed small frame (10 scenes incl. 5 random ones)."""
-    assert len(golden["frames"]) >= 10
+    assert len(golden["frames"]) >= 12
     for key, m in golden["frames"].items():
         img, _ = oracle_frame(m["scene"], m["W"], m["H"], m["depth"])
         assert_bit_identical(img, golden_frames[key], key)
@@ -61,7 +61,7 @@ def test_oracle_txt_md5_other_configs(golden, key):
     ("default", 160, 128, 50), ("default", 64, 36, 5), ("default", 50, 40, 0),
     ("synth1024", 80, 64, 50), ("synth256", 80, 64, 10), ("two_mirrors", 48, 40, 50),
     ("random:11:60", 96, 80, 10), ("random:12:200", 64, 48, 6), ("random:13:15", 96, 80, 30),
-    ("random:14:500", 48, 40, 4),
+    ("random:14:500", 48, 40, 4), ("boxes:1:6", 96, 80, 8), ("boxes:2:10", 80, 64, 20), ("boxes:5:0", 64, 48, 5),
 ])
 def test_oracle_matches_reference_binary(scene, w, h, d):
     """The unmodified reference (calculatePixel & co. compiled from /root/reference/src)."""

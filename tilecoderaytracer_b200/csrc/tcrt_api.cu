@@ -313,6 +313,10 @@ int tcrt_upload_scene(tcrt_ctx* ctx, const tcrt_scene* s, const tcrt_camera* cam
     // type's array is re-ordered into leaf order.  `n_*_nl` keeps meaning "non-light" (the shadow
     // sweep's range); `n_*_bvh` <= n_*_nl is the BVH-covered prefix, the rest is swept linearly.
     std::vector<float4> bvh_s, bvh_f;
+    std::vector<TcrtBoxCluster> clusters;
+    ds.n_fin_gen = ds.n_fin_nl;
+    ds.n_arect = 0;
+    ds.clu_cx = ds.clu_cy = ds.clu_cz = ds.clu_rbig = 0.f;
     ds.bvh_sph_root = ds.bvh_fin_root = 0;
     ds.n_sph_bvh = ds.n_fin_bvh = 0;
     ds.bvh_cx = ds.bvh_cy = ds.bvh_cz = ds.bvh_r2 = ds.bvh_cmax = 0.f;
@@ -374,6 +378,39 @@ int tcrt_upload_scene(tcrt_ctx* ctx, const tcrt_scene* s, const tcrt_camera* cam
             pf.swap(np);
             ds.n_fin_bvh = ds.n_fin_nl;
         }
+        // Axis-aligned finite planes (every makeSceneBox face) are swept through box clusters instead
+        // of one by one (tcrt_cluster.cpp); with a finite-plane BVH the BVH covers them.
+        if (bvh_f.empty() && ds.n_fin_nl > 0) {
+            std::vector<int> cand(pf.begin(), pf.begin() + ds.n_fin_nl), is_arect;
+            tcrt_build_box_clusters(s->fin_geom, cand, is_arect, clusters);
+            if (!clusters.empty()) {
+                std::vector<int> np, new_pos(ds.n_fin_nl, -1);
+                for (int k = 0; k < ds.n_fin_nl; k++)
+                    if (!is_arect[k]) { new_pos[k] = (int)np.size(); np.push_back(pf[k]); }
+                ds.n_fin_gen = (int)np.size();
+                for (int k = 0; k < ds.n_fin_nl; k++)
+                    if (is_arect[k]) { new_pos[k] = (int)np.size(); np.push_back(pf[k]); }
+                ds.n_arect = (int)np.size() - ds.n_fin_gen;
+                np.insert(np.end(), pf.begin() + ds.n_fin_nl, pf.end());
+                pf.swap(np);
+                for (auto& c : clusters) {
+                    for (int f = 0; f < 6; f++)
+                        if (c.plane[f] >= 0) c.plane[f] = new_pos[c.plane[f]];   // -> slot in the finite-plane array
+                    grow(c.lo);   // lo[3], hi[3] are contiguous: a 6-float box
+                }
+            }
+        }
+        if (!clusters.empty()) {
+            double r1 = 0.0, cmax = 0.0;
+            for (int k = 0; k < 3; k++) {
+                r1 += 0.5 * (bhi[k] - blo[k]);
+                cmax = std::max(cmax, std::max(fabs(blo[k]), fabs(bhi[k])));
+            }
+            ds.clu_cx = (float)(0.5 * (blo[0] + bhi[0]));
+            ds.clu_cy = (float)(0.5 * (blo[1] + bhi[1]));
+            ds.clu_cz = (float)(0.5 * (blo[2] + bhi[2]));
+            ds.clu_rbig = (float)((r1 + cmax) * 1.001 + 1e-6);
+        }
         if (!bvh_s.empty() || !bvh_f.empty() || ds.n_sph_bvh || ds.n_fin_bvh) {
             double c[3], r2 = 0.0, cmax = 0.0;
             for (int k = 0; k < 3; k++) {
@@ -391,7 +428,10 @@ int tcrt_upload_scene(tcrt_ctx* ctx, const tcrt_scene* s, const tcrt_camera* cam
     ds.fin_off = ds.n_sph;
     ds.inf_off = ds.fin_off + 4 * ds.n_fin;
     ds.light_off = ds.inf_off + ds.n_inf;
-    ds.idx_off = ds.light_off + 2 * ds.n_lights;
+    ds.n_clu = (int)clusters.size();
+    ds.clu_off = ds.light_off + 2 * ds.n_lights;
+    ds.cslot_off = ds.clu_off + 4 * ds.n_clu;
+    ds.idx_off = ds.cslot_off + (6 * ds.n_clu + 3) / 4;
     const int n_prims = ds.n_sph + ds.n_fin + ds.n_inf;
     ds.blob_f4 = ds.idx_off + (n_prims + 3) / 4;
     if ((size_t)ds.blob_f4 * sizeof(float4) > tcrt_render_max_smem())
@@ -421,6 +461,17 @@ int tcrt_upload_scene(tcrt_ctx* ctx, const tcrt_scene* s, const tcrt_camera* cam
         host[ds.inf_off + k] = f4(s->inf_geom + 16 * pi[k]);
         for (int j = 0; j < 3; j++) host[off_frame + 3 * k + j] = f4(s->inf_geom + 16 * pi[k] + 4 * (j + 1));
         idx[ds.n_sph + ds.n_fin + k] = s->inf_obj[pi[k]];
+    }
+    {
+        int* cslot = reinterpret_cast<int*>(&host[ds.cslot_off]);
+        for (int c = 0; c < ds.n_clu; c++) {
+            const TcrtBoxCluster& b = clusters[c];
+            host[ds.clu_off + 4 * c + 0] = make_float4(b.lo[0], b.lo[1], b.lo[2], b.hi[0]);
+            host[ds.clu_off + 4 * c + 1] = make_float4(b.hi[1], b.hi[2], 0.f, 0.f);
+            host[ds.clu_off + 4 * c + 2] = make_float4(b.c[0], b.c[1], b.c[2], b.c[3]);
+            host[ds.clu_off + 4 * c + 3] = make_float4(b.c[4], b.c[5], 0.f, 0.f);
+            for (int f = 0; f < 6; f++) cslot[6 * c + f] = b.plane[f];
+        }
     }
     for (int l = 0; l < ds.n_lights; l++) {
         const int lo = s->light_obj[l];

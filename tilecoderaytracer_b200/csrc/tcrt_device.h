@@ -17,6 +17,9 @@
 //   [fin_off, fin_off + 4*n_fin)    finite   (n, -dto) (h, h_dist) (v, v_dist) (plane_origin, 0)
 //   [inf_off, inf_off + n_inf)      infinite (n, -dto)
 //   [light_off, light_off + 2*n_lights)  (light position, intensity) (light colour, 0)
+//   [clu_off, clu_off + 4*n_clu)    box clusters of axis-aligned finite planes (tcrt_cluster.cpp):
+//                                   (lo.xyz, hi.x) (hi.yz, -, -) (c of faces x0 x1 y0 y1) (c of z0 z1, -, -)
+//   [cslot_off, ...)                int32 finite-plane slot per cluster face (6 per cluster, -1 = absent)
 //   [idx_off, ...)                  int32 object index per primitive: spheres, finite, infinite
 // Within each type the non-light primitives come first (counts *_nl): the shadow sweep
 // (inShadeCollisionDetection skips lights, RayTracer.cpp:727) just stops there.  The
@@ -30,6 +33,11 @@ struct DeviceScene {
     int n_sph_bvh, n_fin_bvh;           // BVH-covered prefix of the non-light prefix (0 = none)
     int n_lights;
     int fin_off, inf_off, light_off, idx_off;   // float4 offsets into the blob
+    // finite-plane array order: [generic non-light | axis-aligned ("arect", never lights) | lights];
+    // arects are reached through the box clusters only.  n_fin_gen == n_fin_nl - n_arect.
+    int n_fin_gen, n_arect;
+    int n_clu, clu_off, cslot_off;
+    float clu_cx, clu_cy, clu_cz, clu_rbig;   // hull centre of the clusters; L1 radius + largest |coordinate|
     // winner-only, indexed by object index
     const float4* obj_surface;   // colour rgb, diffuse
     const float4* obj_material;  // specular, reflective, intensity, 0
@@ -69,6 +77,20 @@ struct RenderLaunch {
     unsigned long long* counters;   // [0] primary [1] shadow [2] reflect
     unsigned int chunk;      // pixels a warp claims per atomic
 };
+
+// host builder of the box clusters (tcrt_cluster.cpp).  Face f = 2*axis + k; an absent face has
+// c = NaN and plane = -1; `plane` indexes the caller's list.
+struct TcrtBoxCluster {
+    float lo[3], hi[3];
+    float c[6];
+    int plane[6];
+};
+#ifdef __cplusplus
+// planes: indices into fin_geom (16 floats each) of the candidate (non-light) finite planes.
+// arect_of_plane[i] != 0 when planes[i] is axis-aligned and therefore owned by a cluster.
+void tcrt_build_box_clusters(const float* fin_geom, const std::vector<int>& planes, std::vector<int>& arect_of_plane,
+                             std::vector<TcrtBoxCluster>& out);
+#endif
 
 // render kernels (tcrt_render.cu)
 cudaError_t tcrt_launch_render(const RenderLaunch& rl, int sm_count, cudaStream_t stream, int* launches);

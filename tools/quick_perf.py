@@ -18,7 +18,9 @@ ok = True
 if "--noparity" not in sys.argv:
     for name, w, h, d in [("default", 250, 252, 50), ("synth1024", 120, 96, 50), ("synth256", 120, 96, 10),
                           ("random:4:80", 120, 96, 9), ("random:7:120", 120, 96, 9), ("random:24:200", 112, 80, 9),
-                          ("random:27:1500", 64, 48, 6), ("two_mirrors", 64, 48, 50)]:
+                          ("random:27:1500", 64, 48, 6), ("two_mirrors", 64, 48, 50),
+                          ("boxes:1:6", 120, 96, 9), ("boxes:2:10", 120, 96, 12), ("boxes:3:14", 96, 80, 12),
+                          ("boxes:6:9", 120, 96, 9)]:
         cam = api.Camera()
         sc = api.Scene().build(name, cam)
         ctx.upload(sc, cam)
