@@ -185,6 +185,11 @@ int tcrt_flush_l2(tcrt_ctx* ctx);
  * plus the kernel time of each probe.  FFMA counts 1 instruction (2 flops). */
 int tcrt_fp32_peak(tcrt_ctx* ctx, double* unfused_tera_inst, double* fma_tera_inst, double* ms_each);
 
+/* Self-test on device slot 0: the render kernel's shared-reciprocal division (three quotients by one
+ * length, used for vector3d::normalize, vector3d.h:57-74) against the IEEE division instruction
+ * sequence on n_cases pseudo-random operand triples; *n_bad = cases with any differing bit. */
+int tcrt_selftest_div3(tcrt_ctx* ctx, unsigned long long n_cases, unsigned int seed, unsigned long long* n_bad);
+
 /* ---- .txt writer (replaces init_log + printPixelsToLog) --------------------------- */
 /* Bytes of the pixel lines "(%f, %f, %f)\n" of the last render (all its columns). */
 int tcrt_txt_size(tcrt_ctx* ctx, size_t* n_bytes);

@@ -74,6 +74,15 @@ def test_axis_aligned_box_scenes_bit_exact(gpu_ctx, seed, n):
     check_counters(stats, cnt)
 
 
+def test_shared_reciprocal_division_is_ieee(gpu_ctx):
+    """vector3d::normalize divides three components by one length (vector3d.h:57-74); the kernel
+    shares the reciprocal between the three IEEE quotients.  2^31 random operand triples (zeros,
+    denormals, |a| = b, exponents on both sides of the fast-path window) must agree with the
+    division instruction sequence bit for bit."""
+    for seed in (1, 2):
+        assert gpu_ctx.selftest_div3(1 << 30, seed) == 0
+
+
 def test_switches_shadows_reflections(gpu_ctx):
     for kw in ({"shadows": False}, {"reflections": False}, {"shadows": False, "reflections": False}):
         img, stats, want, cnt = gpu_and_oracle(gpu_ctx, "default", 120, 90, 7, **kw)

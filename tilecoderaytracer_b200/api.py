@@ -265,6 +265,12 @@ class Context:
     def flush_l2(self) -> None:
         self._ck(self._lib.tcrt_flush_l2(self._h))
 
+    def selftest_div3(self, n_cases: int, seed: int = 1) -> int:
+        """Mismatches of the kernel's shared-reciprocal division against IEEE division."""
+        bad = C.c_ulonglong(0)
+        self._ck(self._lib.tcrt_selftest_div3(self._h, n_cases, seed, C.byref(bad)))
+        return int(bad.value)
+
     def fp32_peak(self) -> dict:
         """Measured FP32-pipe issue peak of device slot 0 (1e12 lane-instructions/s)."""
         u, f = C.c_double(), C.c_double()

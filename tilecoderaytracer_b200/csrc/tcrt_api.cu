@@ -441,7 +441,7 @@ int tcrt_upload_scene(tcrt_ctx* ctx, const tcrt_scene* s, const tcrt_camera* cam
     const size_t off_surface = (size_t)ds.blob_f4;
     const size_t off_material = off_surface + n;
     const size_t off_normals = off_material + n;
-    const size_t off_frame = off_normals + 2 * (size_t)n;
+    const size_t off_frame = off_normals + 6 * (size_t)n;
     const size_t off_tex = off_frame + 3 * (size_t)ds.n_inf;
     const size_t off_bvh_s = off_tex + 2 * (size_t)s->n_textures;
     const size_t off_bvh_f = off_bvh_s + bvh_s.size();
@@ -467,7 +467,11 @@ int tcrt_upload_scene(tcrt_ctx* ctx, const tcrt_scene* s, const tcrt_camera* cam
         for (int c = 0; c < ds.n_clu; c++) {
             const TcrtBoxCluster& b = clusters[c];
             host[ds.clu_off + 4 * c + 0] = make_float4(b.lo[0], b.lo[1], b.lo[2], b.hi[0]);
-            host[ds.clu_off + 4 * c + 1] = make_float4(b.hi[1], b.hi[2], 0.f, 0.f);
+            int present = 0;
+            for (int f = 0; f < 6; f++) present |= (b.plane[f] >= 0) << f;
+            float4 b1 = make_float4(b.hi[1], b.hi[2], 0.f, 0.f);
+            memcpy(&b1.z, &present, 4);
+            host[ds.clu_off + 4 * c + 1] = b1;
             host[ds.clu_off + 4 * c + 2] = make_float4(b.c[0], b.c[1], b.c[2], b.c[3]);
             host[ds.clu_off + 4 * c + 3] = make_float4(b.c[4], b.c[5], 0.f, 0.f);
             for (int f = 0; f < 6; f++) cslot[6 * c + f] = b.plane[f];
@@ -488,8 +492,21 @@ int tcrt_upload_scene(tcrt_ctx* ctx, const tcrt_scene* s, const tcrt_camera* cam
         if (is_light(i)) flags |= (int)0x80000000u;
         memcpy(&m.w, &flags, sizeof(float));   // bit pattern, read back with __float_as_int
         host[off_material + i] = m;
-        host[off_normals + 2 * i] = f4(s->obj_normals + 8 * i);
-        host[off_normals + 2 * i + 1] = f4(s->obj_normals + 8 * i + 4);
+        // per side (facing, reverse): the normal n1 the collision returns, n2 = normalize(n1) of
+        // Ray(point, normal) (Ray.h:21-25) and N = normalize(n2) of the specular term
+        // (RayTracer.cpp:565-566) — constants of the plane, evaluated here with the reference's
+        // arithmetic (sqrtf, three divisions; this TU is built with -ffp-contract=off)
+        for (int side = 0; side < 2; side++) {
+            float v[3] = {s->obj_normals[8 * i + 4 * side], s->obj_normals[8 * i + 4 * side + 1],
+                          s->obj_normals[8 * i + 4 * side + 2]};
+            for (int rep = 0; rep < 3; rep++) {
+                host[off_normals + 6 * i + 3 * side + rep] = make_float4(v[0], v[1], v[2], 0.f);
+                volatile float len = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);   // vector3d.h:57-74
+                v[0] = v[0] / len;
+                v[1] = v[1] / len;
+                v[2] = v[2] / len;
+            }
+        }
     }
     for (int t = 0; t < s->n_textures; t++) {
         host[off_tex + 2 * t] = f4(s->textures + 8 * t);
@@ -694,6 +711,18 @@ int tcrt_fp32_peak(tcrt_ctx* ctx, double* unfused, double* fma, double* ms_each)
     *unfused = res[0];
     *fma = res[1];
     if (ms_each) { ms_each[0] = ms_out[0]; ms_each[1] = ms_out[1]; }
+    return TCRT_OK;
+}
+
+int tcrt_selftest_div3(tcrt_ctx* ctx, unsigned long long n_cases, unsigned int seed, unsigned long long* n_bad) {
+    if (!ctx || !n_bad) return fail(ctx, TCRT_ERR_INVALID, "null argument");
+    DeviceState& d = ctx->devs[0];
+    CK(ctx, cudaSetDevice(d.dev));
+    CK(ctx, cudaMemsetAsync(d.ctl, 0, 64, d.stream));
+    CK(ctx, tcrt_launch_div3_check(n_cases, seed, reinterpret_cast<unsigned long long*>(d.ctl), d.stream));
+    CK(ctx, cudaMemcpyAsync(d.h_counters, d.ctl, 8, cudaMemcpyDeviceToHost, d.stream));
+    CK(ctx, cudaStreamSynchronize(d.stream));
+    *n_bad = d.h_counters[0];
     return TCRT_OK;
 }
 

@@ -18,7 +18,7 @@
 //   [inf_off, inf_off + n_inf)      infinite (n, -dto)
 //   [light_off, light_off + 2*n_lights)  (light position, intensity) (light colour, 0)
 //   [clu_off, clu_off + 4*n_clu)    box clusters of axis-aligned finite planes (tcrt_cluster.cpp):
-//                                   (lo.xyz, hi.x) (hi.yz, -, -) (c of faces x0 x1 y0 y1) (c of z0 z1, -, -)
+//                                   (lo.xyz, hi.x) (hi.yz, present mask, -) (c of faces x0 x1 y0 y1) (c of z0 z1, -, -)
 //   [cslot_off, ...)                int32 finite-plane slot per cluster face (6 per cluster, -1 = absent)
 //   [idx_off, ...)                  int32 object index per primitive: spheres, finite, infinite
 // Within each type the non-light primitives come first (counts *_nl): the shadow sweep
@@ -41,7 +41,7 @@ struct DeviceScene {
     // winner-only, indexed by object index
     const float4* obj_surface;   // colour rgb, diffuse
     const float4* obj_material;  // specular, reflective, intensity, 0
-    const float4* obj_normals;   // 2 per object: facing normal, reverse normal
+    const float4* obj_normals;   // 6 per object: (n1, normalize(n1), normalize^2(n1)) facing, then reverse
     const int4* obj_info;        // type, slot (position in the permuted type array), is_light, texture id
     const float4* inf_frame;     // 3 per infinite plane slot: horizontal, vertical, origin
     const float4* textures;      // 2 per texture: (light rgb, width) (dark rgb, height)
@@ -94,7 +94,9 @@ void tcrt_build_box_clusters(const float* fin_geom, const std::vector<int>& plan
 
 // render kernels (tcrt_render.cu)
 cudaError_t tcrt_launch_render(const RenderLaunch& rl, int sm_count, cudaStream_t stream, int* launches);
-size_t tcrt_render_max_smem();   // dynamic shared memory the kernel may opt in to
+size_t tcrt_render_max_smem();
+// n random (a.xyz, b) cases: div3 (shared-reciprocal division of the render kernel) vs __fdiv_rn; *bad += mismatches
+cudaError_t tcrt_launch_div3_check(unsigned long long n, unsigned seed, unsigned long long* bad, cudaStream_t stream);   // dynamic shared memory the kernel may opt in to
 
 // txt formatter (tcrt_format.cu)
 // fixed path: 31-byte lines; general path: per-pixel lengths -> two-level exclusive scan
