@@ -481,9 +481,27 @@ int tcrt_upload_scene(tcrt_ctx* ctx, const tcrt_scene* s, const tcrt_camera* cam
         const int lo = s->light_obj[l];
         const float* og = s->obj_origin + 4 * lo;
         const float* sf = s->obj_surface + 4 * lo;
-        // (position, intensity) (material colour, 0): what the light loop reads, RayTracer.cpp:540-563
+        // Shadow rays end at the light.  A cluster whose faces all lie on its hull ("shell": a room)
+        // cannot be crossed by a segment whose two ends are strictly inside the hull; whether the
+        // light is (with twice the kernel's per-ray margin) is a constant: bit c of the mask.
+        unsigned inside_mask = 0u;
+        for (int c = 0; c < ds.n_clu && c < 32; c++) {
+            const TcrtBoxCluster& b = clusters[c];
+            bool shell = true, inside = true;
+            for (int f = 0; f < 6; f++)
+                if (b.plane[f] >= 0 && b.c[f] != b.lo[f / 2] && b.c[f] != b.hi[f / 2]) shell = false;
+            const double l1 = fabs((double)og[0] - ds.clu_cx) + fabs((double)og[1] - ds.clu_cy) +
+                              fabs((double)og[2] - ds.clu_cz) + ds.clu_rbig;
+            const double ml = 2.0 * 4e-6 * l1;   // 2 x TCRT_CLU_K x l1, see tcrt_render.cu clu_ray
+            for (int k = 0; k < 3; k++)
+                if (!((double)og[k] > (double)b.lo[k] + ml && (double)og[k] < (double)b.hi[k] - ml)) inside = false;
+            if (shell && inside) inside_mask |= 1u << c;
+        }
+        // (position, intensity) (material colour, mask): what the light loop reads, RayTracer.cpp:540-563
         host[ds.light_off + 2 * l] = make_float4(og[0], og[1], og[2], s->obj_material[4 * lo + 2]);
-        host[ds.light_off + 2 * l + 1] = make_float4(sf[0], sf[1], sf[2], 0.f);
+        float4 lc = make_float4(sf[0], sf[1], sf[2], 0.f);
+        memcpy(&lc.w, &inside_mask, 4);
+        host[ds.light_off + 2 * l + 1] = lc;
     }
     for (int i = 0; i < n; i++) {
         host[off_surface + i] = f4(s->obj_surface + 4 * i);
