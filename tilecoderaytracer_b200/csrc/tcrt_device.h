@@ -76,6 +76,7 @@ struct RenderLaunch {
     unsigned int* queue;     // pixel queue head (zeroed before launch)
     unsigned long long* counters;   // [0] primary [1] shadow [2] reflect
     unsigned int chunk;      // pixels a warp claims per atomic
+    int refill_min;          // idle lanes a warp waits for before it takes new pixels (1..32)
 };
 
 // host builder of the box clusters (tcrt_cluster.cpp).  Face f = 2*axis + k; an absent face has
