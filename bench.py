@@ -46,6 +46,9 @@ WORKLOADS = {
     "synth256_8k_d10": ("synth256", 7680, 4320, 10),       # configs[4]
     "default_500x504_d50": ("default", 500, 504, 50),      # configs[0], the reference's own case
     "two_mirrors_1080p_d50": ("two_mirrors", 1920, 1080, 50),
+    # reduced-resolution copies of configs[3], [4] for quick ncu captures (tools/profile_run.py)
+    "synth1024_1080p_d50": ("synth1024", 1920, 1080, 50),
+    "synth256_1080p_d10": ("synth256", 1920, 1080, 10),
 }
 DEFAULT_WORKLOAD = "default_1080p_d5"
 METRIC = "Mrays/s (primary+shadow+reflection)"
@@ -216,7 +219,7 @@ def oracle_sample_bands(scene_name, w, h, depth, bands, stride):
 def workload_config(name, n_gpus):
     scene, w, h, depth = WORKLOADS[name]
     return {"workload": name, "scene": scene, "width": w, "height": h, "max_depth": depth, "shadows": True,
-            "reflections": True, "partition": f"{n_gpus} column band(s), one per GPU, no collective",
+            "reflections": True, "partition": f"{n_gpus} cost-balanced column band(s), one per GPU, no collective",
             "l2": "flushed between timed steps (the kernel reads no large input: scene lives in shared memory)"}
 
 
@@ -242,7 +245,10 @@ def run_ours(args):
     params = api.default_params(w, h, depth)
     ctx = api.Context([local])
     ctx.upload(scene, cam)
-    x0, x1 = D.rank_band(w)
+    # one column band per rank; the cut is cost-balanced (a deterministic low-resolution pre-pass
+    # that every rank runs for itself: no communication) and outside the timed region
+    bands = ctx.balance_columns(params, world)
+    x0, x1 = bands[rank]
     flat, camx = scene.flatten(), cam.export()
 
     # ---- warm-up ------------------------------------------------------------------------------------
@@ -308,6 +314,7 @@ def run_ours(args):
         "gpu_launches": launches_total,
         "clocks": clocks.summary(),
         "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps,
+        "bands": [list(b) for b in bands],
     }
 
     if rank == 0:

@@ -177,6 +177,17 @@ int tcrt_download(tcrt_ctx* ctx, float* host_rgb_band);
 /* Device address of a device's band of the last render (for zero-copy consumers, e.g. a
  * torch tensor view); floats = (col_end-col_begin)*height*3. */
 int tcrt_device_frame(tcrt_ctx* ctx, int device_slot, void** dev_ptr, size_t* n_floats);
+/* Cost-balanced column bands (replaces the equal z-bands of the reference's strategy 1,
+ * RayTracer.cpp:904-906, whose load imbalance strategies 2-7 and PixelQueue were written to fix).
+ * Renders a low-resolution copy of the frame on device slot 0 while counting bounces per column,
+ * then cuts [0, width) into n_bands bands of equal estimated cost: bounds[0] = 0 <= bounds[1] <= ...
+ * <= bounds[n_bands] = width.  Deterministic, so every rank of a multi-process run computes the same
+ * cut without communicating.  A multi-device ctx uses the same cut internally. */
+int tcrt_balance_columns(tcrt_ctx* ctx, const tcrt_params* params, int n_bands, int* bounds);
+/* The cut itself (host only, no device needed): costs[i] >= 0 for n_costs equal-width column groups
+ * covering [0, width). */
+int tcrt_bands_from_costs(const double* costs, int n_costs, int width, int n_bands, int* bounds);
+
 /* Overwrite the L2 cache of every device of the ctx (benchmark hygiene between timed steps). */
 int tcrt_flush_l2(tcrt_ctx* ctx);
 /* FP32-pipe microbenchmark on device slot 0 (the roofline denominator of this path, SURVEY

@@ -258,3 +258,26 @@ def test_partition_tiles_the_image():
             assert max(b - a for a, b in bands) - min(b - a for a, b in bands) <= 1
     with pytest.raises(ValueError):
         column_band(10, 2, 2)
+
+
+def test_cost_balanced_bands_tile_and_balance():
+    """tcrt_bands_from_costs (host only): bands tile [0, W), are monotone, and equalise the cost."""
+    from tilecoderaytracer_b200.partition import bands_from_costs, column_bands
+
+    rng = np.random.default_rng(7)
+    for w, n, groups in [(1920, 8, 256), (7680, 8, 256), (500, 3, 250), (64, 8, 64), (5, 8, 5), (1000, 1, 10)]:
+        costs = rng.random(groups) * 10 + (np.arange(groups) > groups // 2) * 30     # right half 4x as expensive
+        bands = bands_from_costs(costs, w, n)
+        assert bands[0][0] == 0 and bands[-1][1] == w
+        assert all(a[1] == b[0] for a, b in zip(bands, bands[1:])) and all(x0 <= x1 for x0, x1 in bands)
+        if w >= 500 and n > 1:
+            per_col = np.repeat(costs, int(np.ceil(w / groups)))[:w] if w % groups else np.repeat(costs, w // groups)
+            load = [per_col[x0:x1].sum() for x0, x1 in bands]
+            assert max(load) <= 1.15 * (sum(load) / n)
+            eq = [per_col[x0:x1].sum() for x0, x1 in column_bands(w, n)]
+            assert max(load) < max(eq)
+    # uniform and all-zero costs give the equal-width cut
+    assert bands_from_costs([1.0] * 64, 640, 4) == column_bands(640, 4)
+    assert bands_from_costs([0.0] * 10, 640, 4) == column_bands(640, 4)
+    with pytest.raises(ValueError):
+        bands_from_costs([1.0, -1.0], 10, 2)

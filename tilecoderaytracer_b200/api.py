@@ -262,6 +262,13 @@ class Context:
         self._ck(self._lib.tcrt_download(self._h, out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def balance_columns(self, params: TcrtParams, n_bands: int) -> list[tuple[int, int]]:
+        """Cost-balanced column bands of the frame (low-resolution pre-pass on device slot 0):
+        [(x0, x1)] * n_bands tiling [0, width).  Deterministic: every rank computes the same cut."""
+        b = (C.c_int * (n_bands + 1))()
+        self._ck(self._lib.tcrt_balance_columns(self._h, C.byref(params), n_bands, b))
+        return [(int(b[i]), int(b[i + 1])) for i in range(n_bands)]
+
     def flush_l2(self) -> None:
         self._ck(self._lib.tcrt_flush_l2(self._h))
 

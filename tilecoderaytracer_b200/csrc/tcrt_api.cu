@@ -3,6 +3,7 @@
 // entry point that needs one fails.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <math.h>
@@ -56,6 +57,10 @@ struct tcrt_ctx {
     bool txt_prepared = false;
     int frame_x0 = 0, frame_x1 = 0, frame_h = 0;
     tcrt_camera cam{};           // passed by value with every launch
+    // cached cost-balanced cut for the multi-device split (tcrt_balance_columns)
+    std::vector<int> cut;
+    tcrt_params cut_params{};
+    bool cut_valid = false;
     char* host_text = nullptr;   // pinned staging for tcrt_write_txt
     size_t host_text_cap = 0;
 };
@@ -551,6 +556,7 @@ int tcrt_upload_scene(tcrt_ctx* ctx, const tcrt_scene* s, const tcrt_camera* cam
         d.ds.bvh_fin = bvh_f.empty() ? nullptr : d.scene_mem + off_bvh_f;
     }
     ctx->cam = *cam;
+    ctx->cut_valid = false;
     ctx->has_scene = true;
     ctx->has_frame = false;
     ctx->txt_prepared = false;
@@ -559,6 +565,8 @@ int tcrt_upload_scene(tcrt_ctx* ctx, const tcrt_scene* s, const tcrt_camera* cam
 
 
 // ---- render -------------------------------------------------------------------------------------
+static int launch_band(tcrt_ctx* ctx, DeviceState& d, const tcrt_params* p, unsigned int* col_cost, int* launches);
+
 static int render_impl(tcrt_ctx* ctx, const tcrt_params* p, int x0, int x1, float* host_band, tcrt_stats* stats) {
     if (!ctx) return fail(ctx, TCRT_ERR_INVALID, "null ctx");
     if (!valid_params(p)) return fail(ctx, TCRT_ERR_INVALID, "bad params");
@@ -572,42 +580,36 @@ static int render_impl(tcrt_ctx* ctx, const tcrt_params* p, int x0, int x1, floa
     ctx->txt_prepared = false;
     int launches = 0;
     // one contiguous band of columns per device (x-major storage makes a band one slice)
+    // (cost-balanced over the whole image when it is rendered whole; equal widths for a sub-range)
+    std::vector<int> cut(nd + 1);
+    for (int i = 0; i <= nd; i++) cut[i] = x0 + (int)((long long)cols * i / nd);
+    if (nd > 1 && x0 == 0 && x1 == p->width) {
+        const bool same = ctx->cut_valid && (int)ctx->cut.size() == nd + 1 && ctx->cut_params.width == p->width &&
+                          ctx->cut_params.height == p->height && ctx->cut_params.max_depth == p->max_depth &&
+                          ctx->cut_params.shadows_on == p->shadows_on && ctx->cut_params.reflections_on == p->reflections_on;
+        if (!same) {
+            ctx->cut.assign(nd + 1, 0);
+            int rc = tcrt_balance_columns(ctx, p, nd, ctx->cut.data());
+            if (rc) return rc;
+            ctx->cut_params = *p;
+            ctx->cut_valid = true;
+        }
+        cut = ctx->cut;
+    }
     for (int i = 0; i < nd; i++) {
         DeviceState& d = ctx->devs[i];
-        d.x0 = x0 + (int)((long long)cols * i / nd);
-        d.x1 = x0 + (int)((long long)cols * (i + 1) / nd);
+        d.x0 = cut[i];
+        d.x1 = cut[i + 1];
         d.height = p->height;
     }
     for (int i = 0; i < nd; i++) {
         DeviceState& d = ctx->devs[i];
         if (d.x1 <= d.x0) continue;
-        CK(ctx, cudaSetDevice(d.dev));
-        const size_t n_floats = (size_t)(d.x1 - d.x0) * p->height * 3;
-        int rc = ensure(ctx, d.frame, d.frame_cap, n_floats);
+        int rc = launch_band(ctx, d, p, nullptr, &launches);
         if (rc) return rc;
-        CK(ctx, cudaMemsetAsync(d.ctl, 0, 64, d.stream));
-        RenderLaunch rl{};
-        rl.scene = d.ds;
-        rl.cam = ctx->cam;
-        rl.width = p->width;
-        rl.height = p->height;
-        rl.x0 = d.x0;
-        rl.x1 = d.x1;
-        rl.max_depth = p->max_depth;
-        rl.shadows_on = p->shadows_on;
-        rl.reflections_on = p->reflections_on;
-        rl.null_r = p->null_color[0];
-        rl.null_g = p->null_color[1];
-        rl.null_b = p->null_color[2];
-        rl.far_dist = p->far_dist;
-        rl.out = d.frame;
-        rl.queue = reinterpret_cast<unsigned int*>(d.ctl);
-        rl.counters = reinterpret_cast<unsigned long long*>(d.ctl + 8);
-        CK(ctx, cudaEventRecord(d.ev_k0, d.stream));
-        CK(ctx, tcrt_launch_render(rl, d.sm_count, d.stream, &launches));
-        CK(ctx, cudaEventRecord(d.ev_k1, d.stream));
         CK(ctx, cudaMemcpyAsync(d.h_counters, d.ctl, 32, cudaMemcpyDeviceToHost, d.stream));
         if (host_band) {
+            const size_t n_floats = (size_t)(d.x1 - d.x0) * p->height * 3;
             float* dst = host_band + (size_t)(d.x0 - x0) * p->height * 3;
             CK(ctx, cudaMemcpyAsync(dst, d.frame, n_floats * sizeof(float), cudaMemcpyDeviceToHost, d.stream));
         }
@@ -645,6 +647,37 @@ static int render_impl(tcrt_ctx* ctx, const tcrt_params* p, int x0, int x1, floa
     return TCRT_OK;
 }
 
+// One device's band [d.x0, d.x1) of the frame `p`: queue reset, kernel, events around it.
+static int launch_band(tcrt_ctx* ctx, DeviceState& d, const tcrt_params* p, unsigned int* col_cost, int* launches) {
+    CK(ctx, cudaSetDevice(d.dev));
+    const size_t n_floats = (size_t)(d.x1 - d.x0) * p->height * 3;
+    int rc = ensure(ctx, d.frame, d.frame_cap, n_floats);
+    if (rc) return rc;
+    CK(ctx, cudaMemsetAsync(d.ctl, 0, 64, d.stream));
+    RenderLaunch rl{};
+    rl.scene = d.ds;
+    rl.cam = ctx->cam;
+    rl.width = p->width;
+    rl.height = p->height;
+    rl.x0 = d.x0;
+    rl.x1 = d.x1;
+    rl.max_depth = p->max_depth;
+    rl.shadows_on = p->shadows_on;
+    rl.reflections_on = p->reflections_on;
+    rl.null_r = p->null_color[0];
+    rl.null_g = p->null_color[1];
+    rl.null_b = p->null_color[2];
+    rl.far_dist = p->far_dist;
+    rl.out = d.frame;
+    rl.queue = reinterpret_cast<unsigned int*>(d.ctl);
+    rl.counters = reinterpret_cast<unsigned long long*>(d.ctl + 8);
+    rl.col_cost = col_cost;
+    CK(ctx, cudaEventRecord(d.ev_k0, d.stream));
+    CK(ctx, tcrt_launch_render(rl, d.sm_count, d.stream, launches));
+    CK(ctx, cudaEventRecord(d.ev_k1, d.stream));
+    return TCRT_OK;
+}
+
 int tcrt_render(tcrt_ctx* ctx, const tcrt_params* p, float* host_rgb, tcrt_stats* stats) {
     if (!host_rgb) return fail(ctx, TCRT_ERR_INVALID, "null output buffer");
     if (!p) return fail(ctx, TCRT_ERR_INVALID, "null params");
@@ -673,6 +706,73 @@ int tcrt_download(tcrt_ctx* ctx, float* host_band) {
         CK(ctx, cudaSetDevice(d.dev));
         CK(ctx, cudaStreamSynchronize(d.stream));
     }
+    return TCRT_OK;
+}
+
+int tcrt_bands_from_costs(const double* costs, int n_costs, int width, int n_bands, int* bounds) {
+    if (!costs || !bounds || n_costs < 1 || width < 0 || n_bands < 1) return TCRT_ERR_INVALID;
+    double total = 0.0;
+    for (int i = 0; i < n_costs; i++) {
+        if (!(costs[i] >= 0.0)) return TCRT_ERR_INVALID;
+        total += costs[i];
+    }
+    bounds[0] = 0;
+    bounds[n_bands] = width;
+    int j = 0;              // current cost group
+    double before = 0.0;    // cost of groups [0, j)
+    for (int k = 1; k < n_bands; k++) {
+        int b;
+        if (!(total > 0.0)) {
+            b = (int)((long long)width * k / n_bands);
+        } else {
+            const double target = total * k / n_bands;
+            while (j < n_costs - 1 && before + costs[j] < target) before += costs[j++];
+            const double frac = costs[j] > 0.0 ? std::min(1.0, std::max(0.0, (target - before) / costs[j])) : 0.0;
+            b = (int)floor(((double)j + frac) * width / n_costs + 0.5);
+        }
+        bounds[k] = std::min(width, std::max(bounds[k - 1], b));
+    }
+    return TCRT_OK;
+}
+
+int tcrt_balance_columns(tcrt_ctx* ctx, const tcrt_params* p, int n_bands, int* bounds) {
+    if (!ctx || !bounds || n_bands < 1) return fail(ctx, TCRT_ERR_INVALID, "bad arguments");
+    if (!valid_params(p)) return fail(ctx, TCRT_ERR_INVALID, "bad params");
+    if (!ctx->has_scene) return fail(ctx, TCRT_ERR_NO_SCENE, "tcrt_upload_scene has not been called");
+    if (p->max_depth > TCRT_MAX_DEPTH) return fail(ctx, TCRT_ERR_UNSUPPORTED, "max_depth too large");
+    if (n_bands == 1) {
+        bounds[0] = 0;
+        bounds[1] = p->width;
+        return TCRT_OK;
+    }
+    // low-resolution copy of the frame: same camera percentages (Camera.cpp:71-84 maps x/W, z/H)
+    tcrt_params lp = *p;
+    lp.width = std::min(p->width, 256);
+    lp.height = std::max(1, std::min(p->height, (int)((long long)p->height * lp.width / std::max(1, p->width))));
+    DeviceState& d = ctx->devs[0];
+    CK(ctx, cudaSetDevice(d.dev));
+    // the pre-pass borrows the device's frame buffer and band bookkeeping
+    ctx->has_frame = false;
+    ctx->txt_prepared = false;
+    d.x0 = 0;
+    d.x1 = lp.width;
+    d.height = lp.height;
+    unsigned int* col_cost = nullptr;
+    CK(ctx, cudaMalloc((void**)&col_cost, sizeof(unsigned int) * lp.width));
+    std::vector<unsigned int> h(lp.width);
+    int launches = 0;
+    int rc = TCRT_OK;
+    cudaError_t e = cudaMemsetAsync(col_cost, 0, sizeof(unsigned int) * lp.width, d.stream);
+    if (e == cudaSuccess) rc = launch_band(ctx, d, &lp, col_cost, &launches);
+    if (e == cudaSuccess && rc == TCRT_OK)
+        e = cudaMemcpyAsync(h.data(), col_cost, sizeof(unsigned int) * lp.width, cudaMemcpyDeviceToHost, d.stream);
+    if (e == cudaSuccess && rc == TCRT_OK) e = cudaStreamSynchronize(d.stream);
+    cudaFree(col_cost);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(ctx, TCRT_ERR_CUDA, "balance pre-pass failed: %s", cudaGetErrorString(e));
+    std::vector<double> costs(h.begin(), h.end());
+    if (tcrt_bands_from_costs(costs.data(), lp.width, p->width, n_bands, bounds) != TCRT_OK)
+        return fail(ctx, TCRT_ERR_INVALID, "bands_from_costs failed");
     return TCRT_OK;
 }
 

@@ -18,3 +18,22 @@ def column_band(width: int, rank: int, world: int) -> tuple[int, int]:
 
 def column_bands(width: int, world: int) -> list[tuple[int, int]]:
     return [column_band(width, r, world) for r in range(world)]
+
+
+def bands_from_costs(costs, width: int, world: int) -> list[tuple[int, int]]:
+    """Cost-balanced cut of [0, width) into `world` bands from per-column-group cost estimates
+    (libtcrt.so: tcrt_bands_from_costs, which tcrt_balance_columns feeds with bounce counts of a
+    low-resolution pre-pass).  The reference answered load imbalance with the TILE64 work queues
+    (PixelQueue.cpp, strategies 2-7); with one band per GPU the band widths do the balancing."""
+    import ctypes as C
+
+    from . import _ffi
+
+    lib = _ffi.load()
+    n = len(costs)
+    arr = (C.c_double * n)(*[float(c) for c in costs])
+    b = (C.c_int * (world + 1))()
+    rc = lib.tcrt_bands_from_costs(arr, n, width, world, b)
+    if rc != 0:
+        raise ValueError("bad cost partition arguments")
+    return [(int(b[i]), int(b[i + 1])) for i in range(world)]
