@@ -245,15 +245,24 @@ def run_ours(args):
     params = api.default_params(w, h, depth)
     ctx = api.Context([local])
     ctx.upload(scene, cam)
-    # one column band per rank; the cut is cost-balanced (a deterministic low-resolution pre-pass
-    # that every rank runs for itself: no communication) and outside the timed region
-    bands = ctx.balance_columns(params, world)
+    # one column band per rank; the cut is cost-balanced (a low-resolution pre-pass on rank 0 that
+    # measures SM clocks per column, shared once at setup) and outside the timed region
+    bands = ctx.balance_columns(params, world) if rank == 0 else None
+    bands = D.broadcast_object(bands)
     x0, x1 = bands[rank]
     flat, camx = scene.flatten(), cam.export()
 
-    # ---- warm-up ------------------------------------------------------------------------------------
-    for _ in range(max(3, args.warmup)):
+    # ---- warm-up (and, at N > 1, feedback on the cut: every rank re-cuts from the same gathered band
+    # times, so all agree; the cut is frozen before the timed region) ---------------------------------
+    from tilecoderaytracer_b200.partition import rebalance
+
+    for i in range(max(3, args.warmup)):
         st = ctx.render_device(params, x0, x1)
+        if world > 1 and i + 1 < max(3, args.warmup):
+            bands = rebalance(bands, D.gather_floats(st.render_ms[0], tdev), w)
+            x0, x1 = bands[rank]
+            if x1 <= x0:
+                raise SystemExit("empty band after rebalancing")
     # ---- timed: K launches, CUDA events around each, L2 flushed in between ------------------------------
     if world > 1:
         import torch
@@ -277,6 +286,7 @@ def run_ours(args):
         D.barrier()
     t_rank_ms = sum(kernel_ms)
     t_ms = D.reduce_max(t_rank_ms, tdev)              # slowest rank, device time
+    rank_ms = [t / args.steps for t in D.gather_floats(t_rank_ms, tdev)]
     rays_total = D.reduce_sum(rays_rank, tdev)        # per frame
     launches_total = int(D.reduce_sum(launches, tdev))
     value = rays_total * args.steps / (t_ms * 1e-3) / 1e6
@@ -314,7 +324,7 @@ def run_ours(args):
         "gpu_launches": launches_total,
         "clocks": clocks.summary(),
         "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps,
-        "bands": [list(b) for b in bands],
+        "bands": [list(b) for b in bands], "kernel_ms_per_rank": rank_ms,
     }
 
     if rank == 0:
@@ -357,6 +367,7 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_baseline(scene_name, w, h, depth)
         print(json.dumps(line))
     ctx.close()
+    D.shutdown()
     return 0
 
 

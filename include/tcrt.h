@@ -179,14 +179,22 @@ int tcrt_download(tcrt_ctx* ctx, float* host_rgb_band);
 int tcrt_device_frame(tcrt_ctx* ctx, int device_slot, void** dev_ptr, size_t* n_floats);
 /* Cost-balanced column bands (replaces the equal z-bands of the reference's strategy 1,
  * RayTracer.cpp:904-906, whose load imbalance strategies 2-7 and PixelQueue were written to fix).
- * Renders a low-resolution copy of the frame on device slot 0 while counting bounces per column,
- * then cuts [0, width) into n_bands bands of equal estimated cost: bounds[0] = 0 <= bounds[1] <= ...
- * <= bounds[n_bands] = width.  Deterministic, so every rank of a multi-process run computes the same
- * cut without communicating.  A multi-device ctx uses the same cut internally. */
+ * Renders a low-resolution copy of the frame on device slot 0 while charging the SM clocks of every
+ * bounce to the columns of the pixels alive in it, then cuts [0, width) into n_bands bands of equal estimated cost: bounds[0] = 0 <= bounds[1] <= ...
+ * <= bounds[n_bands] = width.  The estimate is a measurement (clocks), so two calls may differ by a
+ * column or two: a multi-process run computes the cut on one rank and shares it (bench.py broadcasts
+ * it before the timed region); a multi-device ctx computes it once per (scene, params). */
 int tcrt_balance_columns(tcrt_ctx* ctx, const tcrt_params* params, int n_bands, int* bounds);
 /* The cut itself (host only, no device needed): costs[i] >= 0 for n_costs equal-width column groups
  * covering [0, width). */
 int tcrt_bands_from_costs(const double* costs, int n_costs, int width, int n_bands, int* bounds);
+
+/* Feedback step (host only): given the kernel time ms[b] of every band of the cut `bounds`, the cut
+ * that would equalise the times if cost were spread evenly inside each band.  Applied to consecutive
+ * frames it converges on the measured balance (the role of the reference's self-scheduling
+ * strategies 2/3, RayTracer.cpp:956-1079, between whole GPUs).  A multi-device ctx applies it after
+ * every whole-frame render; bench.py applies it during warm-up. */
+int tcrt_rebalance_columns(const int* bounds, const double* ms, int n_bands, int width, int* new_bounds);
 
 /* Overwrite the L2 cache of every device of the ctx (benchmark hygiene between timed steps). */
 int tcrt_flush_l2(tcrt_ctx* ctx);

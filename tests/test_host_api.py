@@ -281,3 +281,21 @@ def test_cost_balanced_bands_tile_and_balance():
     assert bands_from_costs([0.0] * 10, 640, 4) == column_bands(640, 4)
     with pytest.raises(ValueError):
         bands_from_costs([1.0, -1.0], 10, 2)
+
+
+def test_rebalance_feedback_converges():
+    """tcrt_rebalance_columns (host only): iterating on a synthetic cost profile equalises band times."""
+    from tilecoderaytracer_b200.partition import column_bands, rebalance
+
+    w, n = 1920, 8
+    x = np.arange(w)
+    density = 1.0 + 4.0 * np.exp(-((x - 800) / 150.0) ** 2) + 2.0 * (x > 1500)      # a hot spot and a plateau
+    bands = column_bands(w, n)
+    for _ in range(4):
+        ms = [density[x0:x1].sum() for x0, x1 in bands]
+        bands = rebalance(bands, ms, w)
+        assert bands[0][0] == 0 and bands[-1][1] == w and all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
+    ms = [density[x0:x1].sum() for x0, x1 in bands]
+    assert max(ms) <= 1.03 * (sum(ms) / n)
+    with pytest.raises(ValueError):
+        rebalance([(0, 5), (5, 9)], [1.0, 1.0], 10)

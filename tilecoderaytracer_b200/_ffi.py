@@ -91,6 +91,7 @@ SIGNATURES = {
     "tcrt_flush_l2": (C.c_int, [C.c_void_p]),
     "tcrt_balance_columns": (C.c_int, [C.c_void_p, C.POINTER(TcrtParams), C.c_int, C.POINTER(C.c_int)]),
     "tcrt_bands_from_costs": (C.c_int, [C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "tcrt_rebalance_columns": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "tcrt_selftest_div3": (C.c_int, [C.c_void_p, C.c_ulonglong, C.c_uint, C.POINTER(C.c_ulonglong)]),
     "tcrt_fp32_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "tcrt_txt_size": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t)]),

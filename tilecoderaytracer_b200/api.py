@@ -264,7 +264,7 @@ class Context:
 
     def balance_columns(self, params: TcrtParams, n_bands: int) -> list[tuple[int, int]]:
         """Cost-balanced column bands of the frame (low-resolution pre-pass on device slot 0):
-        [(x0, x1)] * n_bands tiling [0, width).  Deterministic: every rank computes the same cut."""
+        [(x0, x1)] * n_bands tiling [0, width).  A measurement: compute it once and share it."""
         b = (C.c_int * (n_bands + 1))()
         self._ck(self._lib.tcrt_balance_columns(self._h, C.byref(params), n_bands, b))
         return [(int(b[i]), int(b[i + 1])) for i in range(n_bands)]

@@ -565,6 +565,22 @@ int tcrt_upload_scene(tcrt_ctx* ctx, const tcrt_scene* s, const tcrt_camera* cam
 
 
 // ---- render -------------------------------------------------------------------------------------
+int tcrt_rebalance_columns(const int* bounds, const double* ms, int n_bands, int width, int* new_bounds) {
+    if (!bounds || !ms || !new_bounds || n_bands < 1 || width < 0) return TCRT_ERR_INVALID;
+    if (bounds[0] != 0 || bounds[n_bands] != width) return TCRT_ERR_INVALID;
+    std::vector<double> cost((size_t)std::max(width, 1), 0.0);
+    for (int b = 0; b < n_bands; b++) {
+        const int w = bounds[b + 1] - bounds[b];
+        if (w < 0 || !(ms[b] >= 0.0)) return TCRT_ERR_INVALID;
+        for (int x = bounds[b]; x < bounds[b + 1]; x++) cost[x] = ms[b] / w;
+    }
+    if (width == 0) {
+        for (int b = 0; b <= n_bands; b++) new_bounds[b] = 0;
+        return TCRT_OK;
+    }
+    return tcrt_bands_from_costs(cost.data(), width, width, n_bands, new_bounds);
+}
+
 static int launch_band(tcrt_ctx* ctx, DeviceState& d, const tcrt_params* p, unsigned int* col_cost, int* launches);
 
 static int render_impl(tcrt_ctx* ctx, const tcrt_params* p, int x0, int x1, float* host_band, tcrt_stats* stats) {
@@ -639,6 +655,19 @@ static int render_impl(tcrt_ctx* ctx, const tcrt_params* p, int x0, int x1, floa
     if (stats) {
         stats->n_devices = nd;
         stats->gpu_launches = (unsigned long long)launches;
+    }
+    // feedback: the next frame with these params is cut by this frame's measured band times
+    if (nd > 1 && x0 == 0 && x1 == p->width && ctx->cut_valid) {
+        std::vector<double> ms(nd, 0.0);
+        std::vector<int> next(nd + 1, 0);
+        bool ok = true;
+        for (int i = 0; i < nd; i++) {
+            DeviceState& d = ctx->devs[i];
+            float t = 0.f;
+            if (d.x1 > d.x0) ok = ok && cudaEventElapsedTime(&t, d.ev_k0, d.ev_k1) == cudaSuccess;
+            ms[i] = t;
+        }
+        if (ok && tcrt_rebalance_columns(ctx->cut.data(), ms.data(), nd, p->width, next.data()) == TCRT_OK) ctx->cut = next;
     }
     ctx->has_frame = true;
     ctx->frame_x0 = x0;

@@ -75,8 +75,9 @@ struct RenderLaunch {
     float* out;              // (x1-x0)*height*3 floats, x-major
     unsigned int* queue;     // pixel queue head (zeroed before launch)
     unsigned long long* counters;   // [0] primary [1] shadow [2] reflect
-    unsigned int* col_cost;  // optional: per column of the band, += bounces of every finished pixel
-    unsigned int chunk;      // pixels a warp claims per atomic
+    unsigned int* col_cost;  // optional (balancer pre-pass): per column of the band, += bounces of every finished pixel
+    unsigned int chunk;      // most pixels a warp claims per atomic
+    unsigned int claim_div;  // a claim is at most (pixels left) / claim_div
     int refill_min;          // idle lanes a warp waits for before it takes new pixels (1..32)
 };
 

@@ -34,6 +34,14 @@ def init(backend: Optional[str] = None):
     return rank, world, local
 
 
+def shutdown() -> None:
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def barrier() -> None:
     import torch.distributed as dist
 
@@ -50,6 +58,30 @@ def _reduce(value: float, op_name: str, device=None) -> float:
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=getattr(dist.ReduceOp, op_name))
     return float(t.item())
+
+
+def gather_floats(value: float, device=None) -> list[float]:
+    """Every rank's value, in rank order (diagnostics: per-rank kernel times)."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return [float(value)]
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return [float(o.item()) for o in out]
+
+
+def broadcast_object(obj, src: int = 0):
+    """Setup-time only (e.g. the band cut computed on rank 0); never on the render path."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return obj
+    box = [obj]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]
 
 
 def reduce_max(value: float, device=None) -> float:

@@ -37,3 +37,20 @@ def bands_from_costs(costs, width: int, world: int) -> list[tuple[int, int]]:
     if rc != 0:
         raise ValueError("bad cost partition arguments")
     return [(int(b[i]), int(b[i + 1])) for i in range(world)]
+
+
+def rebalance(bands: list[tuple[int, int]], ms: list[float], width: int) -> list[tuple[int, int]]:
+    """Feedback step of the band balancer (libtcrt.so: tcrt_rebalance_columns): the cut that would
+    equalise the measured band times `ms` if cost were uniform inside each band."""
+    import ctypes as C
+
+    from . import _ffi
+
+    lib = _ffi.load()
+    n = len(bands)
+    b = (C.c_int * (n + 1))(*([x0 for x0, _ in bands] + [bands[-1][1]]))
+    t = (C.c_double * n)(*[float(m) for m in ms])
+    out = (C.c_int * (n + 1))()
+    if lib.tcrt_rebalance_columns(b, t, n, width, out) != 0:
+        raise ValueError("bad rebalance arguments")
+    return [(int(out[i]), int(out[i + 1])) for i in range(n)]
