@@ -1,7 +1,10 @@
 // tcrt_api.cu — the C ABI of include/tcrt.h: contexts, scene upload, render launches,
 // copy-back, the .txt writer.  No CPU render path exists here: without a CUDA device every
 // entry point that needs one fails.
+#include <errno.h>
+#include <fcntl.h>
 #include <stdarg.h>
+#include <unistd.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -20,7 +23,9 @@ struct DeviceState {
     int dev = -1;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;           // D2H of finished column chunks, behind the render stream
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_c1 = nullptr;
+    cudaEvent_t ev_chunk[8] = {};                 // chunk k rendered
     // scene
     float4* scene_mem = nullptr;
     size_t scene_cap_f4 = 0;
@@ -116,6 +121,9 @@ void free_device(DeviceState& d) {
     if (d.ev_k0) cudaEventDestroy(d.ev_k0);
     if (d.ev_k1) cudaEventDestroy(d.ev_k1);
     if (d.ev_c1) cudaEventDestroy(d.ev_c1);
+    for (auto& e : d.ev_chunk)
+        if (e) cudaEventDestroy(e);
+    if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
     if (d.stream) cudaStreamDestroy(d.stream);
     d = DeviceState{};
 }
@@ -252,6 +260,9 @@ int tcrt_create(tcrt_ctx** out, const int* device_ids, int n_devices) {
         }
         if (e == cudaSuccess) d.sm_count = prop.multiProcessorCount;
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking);
+        for (auto& ev : d.ev_chunk)
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreate(&d.ev_k0);
         if (e == cudaSuccess) e = cudaEventCreate(&d.ev_k1);
         if (e == cudaSuccess) e = cudaEventCreate(&d.ev_c1);
@@ -581,7 +592,8 @@ int tcrt_rebalance_columns(const int* bounds, const double* ms, int n_bands, int
     return tcrt_bands_from_costs(cost.data(), width, width, n_bands, new_bounds);
 }
 
-static int launch_band(tcrt_ctx* ctx, DeviceState& d, const tcrt_params* p, unsigned int* col_cost, int* launches);
+static int launch_band(tcrt_ctx* ctx, DeviceState& d, const tcrt_params* p, int cx0, int cx1, unsigned int* col_cost,
+                       int* launches);
 
 static int render_impl(tcrt_ctx* ctx, const tcrt_params* p, int x0, int x1, float* host_band, tcrt_stats* stats) {
     if (!ctx) return fail(ctx, TCRT_ERR_INVALID, "null ctx");
@@ -621,15 +633,38 @@ static int render_impl(tcrt_ctx* ctx, const tcrt_params* p, int x0, int x1, floa
     for (int i = 0; i < nd; i++) {
         DeviceState& d = ctx->devs[i];
         if (d.x1 <= d.x0) continue;
-        int rc = launch_band(ctx, d, p, nullptr, &launches);
+        CK(ctx, cudaSetDevice(d.dev));
+        const size_t n_floats = (size_t)(d.x1 - d.x0) * p->height * 3;
+        int rc = ensure(ctx, d.frame, d.frame_cap, n_floats);
         if (rc) return rc;
-        CK(ctx, cudaMemcpyAsync(d.h_counters, d.ctl, 32, cudaMemcpyDeviceToHost, d.stream));
+        CK(ctx, cudaMemsetAsync(d.ctl, 0, 64, d.stream));
+        // With a host destination the band is rendered as up to 8 column chunks; chunk k is copied
+        // back on the copy stream while chunk k+1 renders (the output is x-major: a chunk is one
+        // contiguous slice).  Without one, a single launch.
+        int n_chunks = 1;
         if (host_band) {
-            const size_t n_floats = (size_t)(d.x1 - d.x0) * p->height * 3;
-            float* dst = host_band + (size_t)(d.x0 - x0) * p->height * 3;
-            CK(ctx, cudaMemcpyAsync(dst, d.frame, n_floats * sizeof(float), cudaMemcpyDeviceToHost, d.stream));
+            const long long px = (long long)(d.x1 - d.x0) * p->height;
+            n_chunks = (int)std::min<long long>(std::min<long long>(8, d.x1 - d.x0), std::max<long long>(1, px / (512 * 1024)));
         }
-        CK(ctx, cudaEventRecord(d.ev_c1, d.stream));
+        CK(ctx, cudaEventRecord(d.ev_k0, d.stream));
+        for (int k = 0; k < n_chunks; k++) {
+            const int cx0 = d.x0 + (int)((long long)(d.x1 - d.x0) * k / n_chunks);
+            const int cx1 = d.x0 + (int)((long long)(d.x1 - d.x0) * (k + 1) / n_chunks);
+            if (k > 0) CK(ctx, cudaMemsetAsync(d.ctl, 0, 4, d.stream));   // queue head only; ray counters accumulate
+            rc = launch_band(ctx, d, p, cx0, cx1, nullptr, &launches);
+            if (rc) return rc;
+            if (host_band) {
+                const size_t off = (size_t)(cx0 - d.x0) * p->height * 3;
+                const size_t cnt = (size_t)(cx1 - cx0) * p->height * 3;
+                CK(ctx, cudaEventRecord(d.ev_chunk[k], d.stream));
+                CK(ctx, cudaStreamWaitEvent(d.copy_stream, d.ev_chunk[k], 0));
+                CK(ctx, cudaMemcpyAsync(host_band + (size_t)(d.x0 - x0) * p->height * 3 + off, d.frame + off,
+                                        cnt * sizeof(float), cudaMemcpyDeviceToHost, d.copy_stream));
+            }
+        }
+        CK(ctx, cudaEventRecord(d.ev_k1, d.stream));
+        CK(ctx, cudaMemcpyAsync(d.h_counters, d.ctl, 32, cudaMemcpyDeviceToHost, d.stream));
+        CK(ctx, cudaEventRecord(d.ev_c1, host_band ? d.copy_stream : d.stream));
     }
     if (stats) memset(stats, 0, sizeof(*stats));
     for (int i = 0; i < nd; i++) {
@@ -641,12 +676,13 @@ static int render_impl(tcrt_ctx* ctx, const tcrt_params* p, int x0, int x1, floa
         if (d.x1 <= d.x0) continue;
         CK(ctx, cudaSetDevice(d.dev));
         CK(ctx, cudaStreamSynchronize(d.stream));
+        if (host_band) CK(ctx, cudaStreamSynchronize(d.copy_stream));
         if (stats) {
             float ms = 0.f;
             CK(ctx, cudaEventElapsedTime(&ms, d.ev_k0, d.ev_k1));
             stats->render_ms[i] = ms;
             CK(ctx, cudaEventElapsedTime(&ms, d.ev_k1, d.ev_c1));
-            stats->d2h_ms[i] = host_band ? ms : 0.0;
+            stats->d2h_ms[i] = host_band ? std::max(ms, 0.f) : 0.0;   // copy time not hidden behind the render
             stats->rays_primary[i] = d.h_counters[1];
             stats->rays_shadow[i] = d.h_counters[2];
             stats->rays_reflect[i] = d.h_counters[3];
@@ -676,20 +712,17 @@ static int render_impl(tcrt_ctx* ctx, const tcrt_params* p, int x0, int x1, floa
     return TCRT_OK;
 }
 
-// One device's band [d.x0, d.x1) of the frame `p`: queue reset, kernel, events around it.
-static int launch_band(tcrt_ctx* ctx, DeviceState& d, const tcrt_params* p, unsigned int* col_cost, int* launches) {
-    CK(ctx, cudaSetDevice(d.dev));
-    const size_t n_floats = (size_t)(d.x1 - d.x0) * p->height * 3;
-    int rc = ensure(ctx, d.frame, d.frame_cap, n_floats);
-    if (rc) return rc;
-    CK(ctx, cudaMemsetAsync(d.ctl, 0, 64, d.stream));
+// Columns [cx0, cx1) of device d's band [d.x0, d.x1) of the frame `p`, into the band's frame buffer.
+// The caller has sized the buffer and zeroed the queue head.
+static int launch_band(tcrt_ctx* ctx, DeviceState& d, const tcrt_params* p, int cx0, int cx1, unsigned int* col_cost,
+                       int* launches) {
     RenderLaunch rl{};
     rl.scene = d.ds;
     rl.cam = ctx->cam;
     rl.width = p->width;
     rl.height = p->height;
-    rl.x0 = d.x0;
-    rl.x1 = d.x1;
+    rl.x0 = cx0;
+    rl.x1 = cx1;
     rl.max_depth = p->max_depth;
     rl.shadows_on = p->shadows_on;
     rl.reflections_on = p->reflections_on;
@@ -697,13 +730,11 @@ static int launch_band(tcrt_ctx* ctx, DeviceState& d, const tcrt_params* p, unsi
     rl.null_g = p->null_color[1];
     rl.null_b = p->null_color[2];
     rl.far_dist = p->far_dist;
-    rl.out = d.frame;
+    rl.out = d.frame + (size_t)(cx0 - d.x0) * p->height * 3;
     rl.queue = reinterpret_cast<unsigned int*>(d.ctl);
     rl.counters = reinterpret_cast<unsigned long long*>(d.ctl + 8);
     rl.col_cost = col_cost;
-    CK(ctx, cudaEventRecord(d.ev_k0, d.stream));
     CK(ctx, tcrt_launch_render(rl, d.sm_count, d.stream, launches));
-    CK(ctx, cudaEventRecord(d.ev_k1, d.stream));
     return TCRT_OK;
 }
 
@@ -792,7 +823,9 @@ int tcrt_balance_columns(tcrt_ctx* ctx, const tcrt_params* p, int n_bands, int* 
     int launches = 0;
     int rc = TCRT_OK;
     cudaError_t e = cudaMemsetAsync(col_cost, 0, sizeof(unsigned int) * lp.width, d.stream);
-    if (e == cudaSuccess) rc = launch_band(ctx, d, &lp, col_cost, &launches);
+    if (e == cudaSuccess) rc = ensure(ctx, d.frame, d.frame_cap, (size_t)lp.width * lp.height * 3);
+    if (e == cudaSuccess && rc == TCRT_OK) e = cudaMemsetAsync(d.ctl, 0, 64, d.stream);
+    if (e == cudaSuccess && rc == TCRT_OK) rc = launch_band(ctx, d, &lp, 0, lp.width, col_cost, &launches);
     if (e == cudaSuccess && rc == TCRT_OK)
         e = cudaMemcpyAsync(h.data(), col_cost, sizeof(unsigned int) * lp.width, cudaMemcpyDeviceToHost, d.stream);
     if (e == cudaSuccess && rc == TCRT_OK) e = cudaStreamSynchronize(d.stream);
@@ -1022,10 +1055,23 @@ int tcrt_write_txt(tcrt_ctx* ctx, const tcrt_params* p, const char* path, double
     char header[512];
     int hn = tcrt_txt_header(p, run_time_s, header, sizeof header);
     if (hn < 0) return fail(ctx, TCRT_ERR_INVALID, "header formatting failed");
-    FILE* f = fopen(path, "w");   // log_file_mode "w", RayTracer.h:135
-    if (!f) return fail(ctx, TCRT_ERR_IO, "Error Opening File %s", path);
-    bool ok = fwrite(header, 1, (size_t)hn, f) == (size_t)hn && fwrite(ctx->host_text, 1, total, f) == total;
-    ok = (fclose(f) == 0) && ok;
+    // fopen(path, "w") semantics (log_file_mode "w", RayTracer.h:135): create or truncate.  One
+    // write() per part: the copy into the page cache (~4.5 GB/s on the test box's tmpfs, and not
+    // faster from several threads) is what this step costs.
+    int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0666);
+    if (fd < 0) return fail(ctx, TCRT_ERR_IO, "Error Opening File %s", path);
+    auto write_all = [fd](const char* src, size_t n) {
+        while (n > 0) {
+            ssize_t w = write(fd, src, n);
+            if (w < 0 && errno == EINTR) continue;
+            if (w <= 0) return false;
+            src += w;
+            n -= (size_t)w;
+        }
+        return true;
+    };
+    bool ok = write_all(header, (size_t)hn) && write_all(ctx->host_text, total);
+    ok = (close(fd) == 0) && ok;
     if (!ok) return fail(ctx, TCRT_ERR_IO, "short write to %s", path);
     return TCRT_OK;
 }
