@@ -8,6 +8,7 @@
 // Binary tree, surface-area heuristic with a full sweep on each axis, leaves of <= 4 primitives
 // (<= 8 when splitting does not pay), depth capped at 40 by falling back to median splits.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -41,6 +42,7 @@ struct Builder {
     std::vector<int>& order;       // permuted in place
     std::vector<float4>& nodes;
     std::vector<double> suffix;
+    int max_leaf = 4;
 
     Builder(const float* b, std::vector<int>& o, std::vector<float4>& n) : boxes(b), order(o), nodes(n) {}
 
@@ -59,7 +61,7 @@ struct Builder {
 
     // returns the encoded reference of the subtree over order[first, first+count)
     int build(int first, int count, int depth) {
-        if (count <= 4) return leaf_ref(first, count);
+        if (count <= max_leaf) return leaf_ref(first, count);
         const Box parent = bounds(first, count);
         int best_axis = -1, best_split = -1;
         double best_cost = 1e308;
@@ -83,7 +85,7 @@ struct Builder {
                 }
             }
             // no split beats a leaf: keep small groups together
-            if (count <= 8 && best_cost >= parent.area() * count) return leaf_ref(first, count);
+            if (count <= 2 * max_leaf && best_cost >= parent.area() * count) return leaf_ref(first, count);
         }
         if (best_axis < 0) {   // depth guard: balanced median split on the widest centroid axis
             float clo[3] = {INFINITY, INFINITY, INFINITY}, chi[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -125,5 +127,6 @@ int tcrt_build_bvh(const std::vector<float>& boxes, int n, std::vector<int>& ord
     for (int i = 0; i < n; i++) order[i] = i;
     nodes.clear();
     Builder b(boxes.data(), order, nodes);
+    if (const char* e = getenv("TCRT_BVH_LEAF")) b.max_leaf = std::max(1, std::min(8, atoi(e)));   // developer knob
     return b.build(0, n, 0);
 }
