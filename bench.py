@@ -252,17 +252,25 @@ def run_ours(args):
     x0, x1 = bands[rank]
     flat, camx = scene.flatten(), cam.export()
 
-    # ---- warm-up (and, at N > 1, feedback on the cut: every rank re-cuts from the same gathered band
-    # times, so all agree; the cut is frozen before the timed region) ---------------------------------
+    # ---- at N > 1, feedback on the cut: every rank re-cuts from the same gathered band times (so all
+    # agree) until the slowest band is within 1 % of the mean; the cut is then frozen -------------------
     from tilecoderaytracer_b200.partition import rebalance
 
-    for i in range(max(3, args.warmup)):
-        st = ctx.render_device(params, x0, x1)
-        if world > 1 and i + 1 < max(3, args.warmup):
-            bands = rebalance(bands, D.gather_floats(st.render_ms[0], tdev), w)
+    balance_log = []
+    if world > 1:
+        for it in range(16):
+            ms = min(ctx.render_device(params, x0, x1).render_ms[0] for _ in range(2))
+            all_ms = D.gather_floats(ms, tdev)
+            balance_log.append(max(all_ms) / (sum(all_ms) / world))
+            if balance_log[-1] < 1.01:
+                break
+            bands = rebalance(bands, all_ms, w)
             x0, x1 = bands[rank]
             if x1 <= x0:
                 raise SystemExit("empty band after rebalancing")
+    # ---- warm-up ------------------------------------------------------------------------------------
+    for i in range(max(3, args.warmup)):
+        st = ctx.render_device(params, x0, x1)
     # ---- timed: K launches, CUDA events around each, L2 flushed in between ------------------------------
     if world > 1:
         import torch
@@ -325,6 +333,7 @@ def run_ours(args):
         "clocks": clocks.summary(),
         "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps,
         "bands": [list(b) for b in bands], "kernel_ms_per_rank": rank_ms,
+        "balance_max_over_mean_per_iteration": balance_log,
     }
 
     if rank == 0:
