@@ -336,6 +336,27 @@ def run_ours(args):
         "balance_max_over_mean_per_iteration": balance_log,
     }
 
+    if world == 1:
+        # ---- multi-frame mode: scene resident, a new camera per frame, frame to the host ----
+        import copy
+
+        n_mf = e2e_steps
+        cams = []
+        for i in range(n_mf):
+            c = copy.copy(camx)
+            c.eye[0] = camx.eye[0] + 0.002 * i       # a slow dolly: every frame is a different image
+            cams.append(c)
+        ctx.set_camera(cams[0])
+        ctx.render(params, x0, x1, out)
+        t0 = time.perf_counter()
+        for c in cams:
+            ctx.set_camera(c)
+            ctx.render(params, x0, x1, out)
+        mf_s = time.perf_counter() - t0
+        ctx.set_camera(camx)
+        line["e2e_multiframe"] = {"frames_per_s": n_mf / mf_s, "frames": n_mf,
+                                  "what": "tcrt_set_camera + tcrt_render_columns into pinned host memory per frame; "
+                                          "scene stays on the device"}
     if rank == 0:
         # ---- .txt writer leg (the reference's output format), N=1 only --------------------------------------
         if world == 1:

@@ -204,6 +204,20 @@ int tcrt_flush_l2(tcrt_ctx* ctx);
  * plus the kernel time of each probe.  FFMA counts 1 instruction (2 flops). */
 int tcrt_fp32_peak(tcrt_ctx* ctx, double* unfused_tera_inst, double* fma_tera_inst, double* ms_each);
 
+/* ---- beyond the reference ------------------------------------------------------------ */
+/* Multi-frame mode: replaces the camera of the uploaded scene without touching the scene (the
+ * reference renders one static frame and lists moving scenes as unsupported, README.md:29).  The
+ * camera travels with every launch, so this is free; the next render uses it. */
+int tcrt_set_camera(tcrt_ctx* ctx, const tcrt_camera* camera);
+/* The last render as a binary PPM (P6, 8 bits per channel, q(c) = floor(clamp(c,0,1)*255 + 0.5)),
+ * viewable directly: image column = x, image row 0 = the TOP (z = height-1), as the reference's
+ * offline viewer would show the .txt.  Quantised on the GPU, 3 B/pixel cross the bus. */
+int tcrt_write_ppm(tcrt_ctx* ctx, const tcrt_params* params, const char* path);
+/* The last render as raw little-endian float32 (the binary output the reference leaves as a TODO,
+ * RayTracer.cpp:1605-1613): a 32-byte header "TCRTBIN1" + int32 width, height + 16 zero bytes, then
+ * width*height*3 floats in the order of pixels[W][H] (x-major, z fastest, r g b). */
+int tcrt_write_bin(tcrt_ctx* ctx, const tcrt_params* params, const char* path);
+
 /* Self-test on device slot 0: the render kernel's shared-reciprocal division (three quotients by one
  * length, used for vector3d::normalize, vector3d.h:57-74) against the IEEE division instruction
  * sequence on n_cases pseudo-random operand triples; *n_bad = cases with any differing bit. */

@@ -52,6 +52,17 @@ int tcrt_hobj_set_light(tcrt_hscene* s, int obj, float intensity);              
 int tcrt_hobj_set_checker(tcrt_hscene* s, int obj, const float* light_rgb3, const float* dark_rgb3, float width,
                           float height);                                                     /* Texture_CheckerBoard + setTexture */
 
+/* Text scene description -> the same construction calls (the reference hard-codes its
+ * scenes and lists a loader as a TODO, rt_project_parameters.h:31-32).  One statement per line,
+ * '#' starts a comment, numbers are C floats (decimal or hex-float):
+ *   sphere cx cy cz r | infinite_plane o(3) n(3) h(3) | finite_plane_corners o(3) vcorner(3) hcorner(3)
+ *   finite_plane_axes o(3) n(3) h(3) v_dist h_dist | box o(3) dims(3)          -- primitives
+ *   color r g b | diffuse f | specular f | reflective f | light intensity
+ *   checker lr lg lb dr dg db width height            -- apply to the objects of the last primitive line
+ *   camera two_mirrors                                -- Camera::setSceneTwoMirrors()
+ * Returns 0, or TCRT_ERR_INVALID / TCRT_ERR_IO with a message ("line N: ...") in err (may be NULL). */
+int tcrt_hscene_load_text(tcrt_hscene* s, tcrt_hcamera* c, const char* path, char* err, size_t err_cap);
+
 /* Scene::flatten(): fills *out with pointers into storage owned by the handle, valid until
  * the next flatten / mutation / free of the handle. */
 int tcrt_hscene_flatten(tcrt_hscene* s, tcrt_scene* out);

@@ -353,6 +353,37 @@ def test_cost_balanced_bands_on_gpu(gpu_ctx):
         assert max(rays_bal) <= 1.25 * st.rays / n
 
 
+def test_image_outputs_and_camera_update(gpu_ctx, tmp_path):
+    """PPM / raw-float outputs of a frame and tcrt_set_camera (multi-frame mode)."""
+    scene, cam = make_scene("default")
+    p = api.default_params(96, 64, 6)
+    gpu_ctx.upload(scene, cam)
+    img, _ = gpu_ctx.render(p)
+    gpu_ctx.write_ppm(p, str(tmp_path / "a.ppm"))
+    raw = (tmp_path / "a.ppm").read_bytes()
+    head = b"P6\n96 64\n255\n"
+    assert raw.startswith(head) and len(raw) == len(head) + 96 * 64 * 3
+    got = np.frombuffer(raw[len(head):], dtype=np.uint8).reshape(64, 96, 3)
+    want = np.transpose(quant8(img), (1, 0, 2))[::-1].astype(np.uint8)
+    assert np.array_equal(got, want)
+    gpu_ctx.write_bin(p, str(tmp_path / "a.bin"))
+    rawb = (tmp_path / "a.bin").read_bytes()
+    assert rawb[:8] == b"TCRTBIN1" and np.frombuffer(rawb[8:16], dtype=np.int32).tolist() == [96, 64]
+    assert np.array_equal(np.frombuffer(rawb[32:], dtype=np.float32).view(np.uint32), bits(img).ravel())
+    # a moved camera without re-uploading the scene == uploading with that camera
+    cam2 = cam.export()
+    cam2.eye[0] += 0.25
+    cam2.eye[2] += 0.1
+    gpu_ctx.set_camera(cam2)
+    moved, _ = gpu_ctx.render(p)
+    assert n_mismatch(moved, img) > 0
+    gpu_ctx.upload_flat(scene.flatten(), cam2)
+    again, _ = gpu_ctx.render(p)
+    assert_bit_identical(moved, again, "set_camera vs upload")
+    want2, _ = O.render(scene.flatten(), cam2, p)
+    assert_bit_identical(moved, want2, "moved camera vs oracle")
+
+
 def test_multi_device_context_if_available(gpu_ctx):
     """In-process band split over every visible GPU: same bits as one GPU."""
     n = api.device_count()

@@ -299,3 +299,66 @@ def test_rebalance_feedback_converges():
     assert max(ms) <= 1.03 * (sum(ms) / n)
     with pytest.raises(ValueError):
         rebalance([(0, 5), (5, 9)], [1.0, 1.0], 10)
+
+
+def test_text_scene_loader_reproduces_the_default_scene(tmp_path):
+    """scenes/default.scene through tcrt_hscene_load_text flattens to exactly the arrays of
+    Scene::initialize() (Scene.cpp:209-387); errors carry the line number."""
+    import ctypes as C
+    import os
+
+    from tilecoderaytracer_b200 import _ffi
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sa = api.Scene().initialize()       # the flattened views point into storage owned by the scenes
+    sb = api.Scene().load_text(os.path.join(root, "scenes", "default.scene"))
+    a, b = sa.flatten(), sb.flatten()
+    for name, ctype in _ffi.TcrtScene._fields_:
+        va, vb = getattr(a, name), getattr(b, name)
+        if isinstance(va, int):
+            assert va == vb, name
+    n = a.n_objects
+    sizes = {"sphere_geom": 4 * a.n_spheres, "fin_geom": 16 * a.n_fin_planes, "inf_geom": 16 * a.n_inf_planes,
+             "obj_surface": 4 * n, "obj_material": 4 * n, "obj_origin": 4 * n, "obj_normals": 8 * n,
+             "textures": 8 * a.n_textures}
+    for name, cnt in sizes.items():
+        xa = np.ctypeslib.as_array(getattr(a, name), (cnt,)).view(np.uint32)
+        xb = np.ctypeslib.as_array(getattr(b, name), (cnt,)).view(np.uint32)
+        assert np.array_equal(xa, xb), name
+    for name, cnt in {"obj_info": 4 * n, "sphere_obj": a.n_spheres, "fin_obj": a.n_fin_planes,
+                      "inf_obj": a.n_inf_planes, "light_obj": a.n_lights}.items():
+        assert np.array_equal(np.ctypeslib.as_array(getattr(a, name), (cnt,)),
+                              np.ctypeslib.as_array(getattr(b, name), (cnt,))), name
+    bad = tmp_path / "bad.scene"
+    bad.write_text("sphere 0 0 0 1\ncolor 1 0\n")
+    with pytest.raises(api.TcrtError, match="line 2"):
+        api.Scene().load_text(str(bad))
+    bad.write_text("color 1 0 0\n")
+    with pytest.raises(api.TcrtError, match="before any primitive"):
+        api.Scene().load_text(str(bad))
+    with pytest.raises(api.TcrtError):
+        api.Scene().load_text(str(tmp_path / "missing.scene"))
+
+
+def test_txt_to_ppm_tool(tmp_path):
+    """tools/txt_to_ppm.py (the offline viewer replacement): tags + pixel lines -> PPM rows, top first."""
+    import importlib.util
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("txt_to_ppm", os.path.join(root, "tools", "txt_to_ppm.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    w, h = 3, 2
+    px = np.zeros((w, h, 3))
+    px[0, 0] = (1.0, 0.5, 0.0)       # bottom-left
+    px[2, 1] = (2.5, 0.25, 0.999)    # top-right, over-range red
+    p = api.default_params(w, h, 5)
+    txt = api.txt_header(p, 0.0) + b"".join(b"(%f, %f, %f)\n" % tuple(px[x, z]) for x in range(w) for z in range(h))
+    path = tmp_path / "s.txt"
+    path.write_bytes(txt)
+    gw, gh, got, tags = mod.read_txt(str(path))
+    assert (gw, gh) == (w, h) and np.allclose(got, px) and tags["Hardware_Target"] == "OSX C++"
+    img = mod.to_image(mod.quant8(got))
+    assert img.shape == (h, w, 3)
+    assert tuple(img[1, 0]) == (255, 128, 0) and tuple(img[0, 2]) == (255, 64, 255)

@@ -92,6 +92,9 @@ SIGNATURES = {
     "tcrt_balance_columns": (C.c_int, [C.c_void_p, C.POINTER(TcrtParams), C.c_int, C.POINTER(C.c_int)]),
     "tcrt_bands_from_costs": (C.c_int, [C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     "tcrt_rebalance_columns": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "tcrt_set_camera": (C.c_int, [C.c_void_p, C.POINTER(TcrtCamera)]),
+    "tcrt_write_ppm": (C.c_int, [C.c_void_p, C.POINTER(TcrtParams), C.c_char_p]),
+    "tcrt_write_bin": (C.c_int, [C.c_void_p, C.POINTER(TcrtParams), C.c_char_p]),
     "tcrt_selftest_div3": (C.c_int, [C.c_void_p, C.c_ulonglong, C.c_uint, C.POINTER(C.c_ulonglong)]),
     "tcrt_fp32_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "tcrt_txt_size": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t)]),
@@ -109,6 +112,7 @@ SIGNATURES = {
     "tcrt_hcamera_export": (None, [C.c_void_p, C.POINTER(TcrtCamera)]),
     "tcrt_hcamera_eye_ray": (None, [C.c_void_p, C.c_float, C.c_float, c_float_p, c_float_p]),
     "tcrt_hscene_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p]),
+    "tcrt_hscene_load_text": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p, C.c_char_p, C.c_size_t]),
     "tcrt_hscene_add_sphere": (C.c_int, [C.c_void_p, c_float_p, C.c_float]),
     "tcrt_hscene_add_infinite_plane": (C.c_int, [C.c_void_p, c_float_p, c_float_p, c_float_p]),
     "tcrt_hscene_add_finite_plane_corners": (C.c_int, [C.c_void_p, c_float_p, c_float_p, c_float_p]),

@@ -103,6 +103,14 @@ class Scene:
             raise TcrtError(rc, f"cannot build scene {name!r}")
         return self
 
+    def load_text(self, path: str, camera: Optional[Camera] = None) -> "Scene":
+        """Text scene description (format: include/tcrt_host.h, example: scenes/default.scene)."""
+        err = C.create_string_buffer(256)
+        rc = self._lib.tcrt_hscene_load_text(self._h, camera._h if camera else None, path.encode(), err, 256)
+        if rc != 0:
+            raise TcrtError(rc, f"{path}: {err.value.decode()}")
+        return self
+
     def initialize(self) -> "Scene":
         return self.build("default")
 
@@ -314,6 +322,18 @@ class Context:
 
     def write_txt(self, params: TcrtParams, path: str, run_time_s: float = 0.0) -> None:
         self._ck(self._lib.tcrt_write_txt(self._h, C.byref(params), path.encode(), run_time_s))
+
+    def write_ppm(self, params: TcrtParams, path: str) -> None:
+        """The last render as an 8-bit binary PPM (row 0 = top of the image)."""
+        self._ck(self._lib.tcrt_write_ppm(self._h, C.byref(params), path.encode()))
+
+    def write_bin(self, params: TcrtParams, path: str) -> None:
+        """The last render as raw float32 ("TCRTBIN1" header + pixels[W][H] order)."""
+        self._ck(self._lib.tcrt_write_bin(self._h, C.byref(params), path.encode()))
+
+    def set_camera(self, cam: TcrtCamera) -> None:
+        """Multi-frame mode: new camera, same resident scene."""
+        self._ck(self._lib.tcrt_set_camera(self._h, C.byref(cam)))
 
 
 def txt_header(params: TcrtParams, run_time_s: float) -> bytes:

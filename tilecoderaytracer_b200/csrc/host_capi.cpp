@@ -2,6 +2,7 @@
 #include "tcrt_host.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "CelioRayTracer.hpp"
@@ -144,6 +145,80 @@ int tcrt_hobj_set_checker(tcrt_hscene* s, int i, const float* l, const float* d,
     t->setWidth(width);
     o->getMaterial()->setTexture(t);   // like the reference, textures are never freed
     return TCRT_OK;
+}
+
+int tcrt_hscene_load_text(tcrt_hscene* s, tcrt_hcamera* c, const char* path, char* err, size_t err_cap) {
+    auto fail = [&](int code, int line, const char* msg) {
+        if (err && err_cap) snprintf(err, err_cap, "line %d: %s", line, msg);
+        return code;
+    };
+    if (!s || !path) return fail(TCRT_ERR_INVALID, 0, "null argument");
+    FILE* f = fopen(path, "r");
+    if (!f) return fail(TCRT_ERR_IO, 0, "cannot open scene file");
+    char buf[1024];
+    int line = 0, first = -1, count = 0;   // objects created by the last primitive line
+    int rc = TCRT_OK;
+    while (rc == TCRT_OK && fgets(buf, sizeof buf, f)) {
+        line++;
+        if (char* hash = strchr(buf, '#')) *hash = 0;
+        char* save = NULL;
+        char* kw = strtok_r(buf, " \t\r\n", &save);
+        if (!kw) continue;
+        float v[16];
+        int n = 0;
+        char* tok;
+        bool bad = false;
+        char word[64] = "";
+        while ((tok = strtok_r(NULL, " \t\r\n", &save)) != NULL) {
+            char* end = NULL;
+            float x = strtof(tok, &end);
+            if (end == tok || *end != 0) {
+                if (n == 0 && !word[0]) { snprintf(word, sizeof word, "%s", tok); continue; }
+                bad = true;
+                break;
+            }
+            if (n < 16) v[n] = x;
+            n++;
+        }
+        if (bad) { rc = fail(TCRT_ERR_INVALID, line, "not a number"); break; }
+        auto need = [&](int k) { return n == k && !word[0]; };
+        auto created = [&](int idx, int cnt) {
+            if (idx < 0) return fail(TCRT_ERR_INVALID, line, "scene is full");
+            first = idx;
+            count = cnt;
+            return (int)TCRT_OK;
+        };
+        auto each = [&](int (*fn)(tcrt_hscene*, int, float), float x) {
+            if (first < 0) return fail(TCRT_ERR_INVALID, line, "material statement before any primitive");
+            for (int i = first; i < first + count; i++) fn(s, i, x);
+            return (int)TCRT_OK;
+        };
+        if (!strcmp(kw, "sphere") && need(4)) rc = created(tcrt_hscene_add_sphere(s, v, v[3]), 1);
+        else if (!strcmp(kw, "infinite_plane") && need(9)) rc = created(tcrt_hscene_add_infinite_plane(s, v, v + 3, v + 6), 1);
+        else if (!strcmp(kw, "finite_plane_corners") && need(9))
+            rc = created(tcrt_hscene_add_finite_plane_corners(s, v, v + 3, v + 6), 1);
+        else if (!strcmp(kw, "finite_plane_axes") && need(11))
+            rc = created(tcrt_hscene_add_finite_plane_axes(s, v, v + 3, v + 6, v[9], v[10]), 1);
+        else if (!strcmp(kw, "box") && need(6)) rc = created(tcrt_hscene_add_box(s, v, v + 3), 6);
+        else if (!strcmp(kw, "diffuse") && need(1)) rc = each(tcrt_hobj_set_diffuse, v[0]);
+        else if (!strcmp(kw, "specular") && need(1)) rc = each(tcrt_hobj_set_specular, v[0]);
+        else if (!strcmp(kw, "reflective") && need(1)) rc = each(tcrt_hobj_set_reflective, v[0]);
+        else if (!strcmp(kw, "light") && need(1)) rc = each(tcrt_hobj_set_light, v[0]);
+        else if (!strcmp(kw, "color") && need(3)) {
+            if (first < 0) rc = fail(TCRT_ERR_INVALID, line, "material statement before any primitive");
+            for (int i = first; rc == TCRT_OK && i < first + count; i++) tcrt_hobj_set_color(s, i, v[0], v[1], v[2]);
+        } else if (!strcmp(kw, "checker") && need(8)) {
+            if (first < 0) rc = fail(TCRT_ERR_INVALID, line, "material statement before any primitive");
+            for (int i = first; rc == TCRT_OK && i < first + count; i++) tcrt_hobj_set_checker(s, i, v, v + 3, v[6], v[7]);
+        } else if (!strcmp(kw, "camera") && n == 0 && !strcmp(word, "two_mirrors")) {
+            if (!c) rc = fail(TCRT_ERR_INVALID, line, "no camera handle given");
+            else tcrt_hcamera_set_two_mirrors(c);
+        } else {
+            rc = fail(TCRT_ERR_INVALID, line, "unknown statement or wrong number of arguments");
+        }
+    }
+    fclose(f);
+    return rc;
 }
 
 int tcrt_hscene_flatten(tcrt_hscene* s, tcrt_scene* out) {

@@ -894,6 +894,93 @@ int tcrt_fp32_peak(tcrt_ctx* ctx, double* unfused, double* fma, double* ms_each)
     return TCRT_OK;
 }
 
+int tcrt_set_camera(tcrt_ctx* ctx, const tcrt_camera* cam) {
+    if (!ctx || !cam) return fail(ctx, TCRT_ERR_INVALID, "null argument");
+    if (!ctx->has_scene) return fail(ctx, TCRT_ERR_NO_SCENE, "tcrt_upload_scene has not been called");
+    ctx->cam = *cam;
+    ctx->cut_valid = false;
+    return TCRT_OK;
+}
+
+static int check_full_frame(tcrt_ctx* ctx, const tcrt_params* p) {
+    if (!ctx->has_frame) return fail(ctx, TCRT_ERR_NO_FRAME, "nothing rendered yet");
+    if (ctx->frame_x0 != 0 || ctx->frame_x1 != p->width || ctx->frame_h != p->height)
+        return fail(ctx, TCRT_ERR_INVALID, "last render covered columns [%d,%d) x %d, not the %dx%d image", ctx->frame_x0,
+                    ctx->frame_x1, ctx->frame_h, p->width, p->height);
+    return TCRT_OK;
+}
+
+static bool write_fully(int fd, const void* src, size_t n) {
+    const char* s = static_cast<const char*>(src);
+    while (n > 0) {
+        ssize_t w = write(fd, s, n);
+        if (w < 0 && errno == EINTR) continue;
+        if (w <= 0) return false;
+        s += w;
+        n -= (size_t)w;
+    }
+    return true;
+}
+
+int tcrt_write_ppm(tcrt_ctx* ctx, const tcrt_params* p, const char* path) {
+    if (!ctx || !p || !path) return fail(ctx, TCRT_ERR_INVALID, "null argument");
+    int rc = check_full_frame(ctx, p);
+    if (rc) return rc;
+    const size_t W = (size_t)p->width, H = (size_t)p->height;
+    std::vector<unsigned char> xmajor(W * H * 3);
+    // quantise each band on its device (the text scratch buffer doubles as the 8-bit staging area)
+    for (auto& d : ctx->devs) {
+        if (d.x1 <= d.x0) continue;
+        CK(ctx, cudaSetDevice(d.dev));
+        const size_t nv = (size_t)(d.x1 - d.x0) * H * 3;
+        rc = ensure(ctx, d.text, d.text_cap, nv + 16);
+        if (rc) return rc;
+        ctx->txt_prepared = false;
+        CK(ctx, tcrt_launch_quantize8(d.frame, nv, reinterpret_cast<unsigned char*>(d.text), d.stream));
+        CK(ctx, cudaMemcpyAsync(xmajor.data() + (size_t)d.x0 * H * 3, d.text, nv, cudaMemcpyDeviceToHost, d.stream));
+    }
+    for (auto& d : ctx->devs) {
+        if (d.x1 <= d.x0) continue;
+        CK(ctx, cudaSetDevice(d.dev));
+        CK(ctx, cudaStreamSynchronize(d.stream));
+    }
+    // x-major, z up  ->  image rows, top row first
+    std::vector<unsigned char> img(W * H * 3);
+    for (size_t x = 0; x < W; x++)
+        for (size_t z = 0; z < H; z++) {
+            const unsigned char* s = &xmajor[(x * H + z) * 3];
+            unsigned char* o = &img[((H - 1 - z) * W + x) * 3];
+            o[0] = s[0]; o[1] = s[1]; o[2] = s[2];
+        }
+    char header[64];
+    const int hn = snprintf(header, sizeof header, "P6\n%d %d\n255\n", p->width, p->height);
+    int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0666);
+    if (fd < 0) return fail(ctx, TCRT_ERR_IO, "Error Opening File %s", path);
+    bool ok = write_fully(fd, header, (size_t)hn) && write_fully(fd, img.data(), img.size());
+    ok = (close(fd) == 0) && ok;
+    if (!ok) return fail(ctx, TCRT_ERR_IO, "short write to %s", path);
+    return TCRT_OK;
+}
+
+int tcrt_write_bin(tcrt_ctx* ctx, const tcrt_params* p, const char* path) {
+    if (!ctx || !p || !path) return fail(ctx, TCRT_ERR_INVALID, "null argument");
+    int rc = check_full_frame(ctx, p);
+    if (rc) return rc;
+    const size_t n = (size_t)p->width * p->height * 3;
+    std::vector<float> host(n);
+    rc = tcrt_download(ctx, host.data());
+    if (rc) return rc;
+    unsigned char header[32] = {'T', 'C', 'R', 'T', 'B', 'I', 'N', '1'};
+    const int wh[2] = {p->width, p->height};
+    memcpy(header + 8, wh, 8);
+    int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0666);
+    if (fd < 0) return fail(ctx, TCRT_ERR_IO, "Error Opening File %s", path);
+    bool ok = write_fully(fd, header, sizeof header) && write_fully(fd, host.data(), n * sizeof(float));
+    ok = (close(fd) == 0) && ok;
+    if (!ok) return fail(ctx, TCRT_ERR_IO, "short write to %s", path);
+    return TCRT_OK;
+}
+
 int tcrt_selftest_div3(tcrt_ctx* ctx, unsigned long long n_cases, unsigned int seed, unsigned long long* n_bad) {
     if (!ctx || !n_bad) return fail(ctx, TCRT_ERR_INVALID, "null argument");
     DeviceState& d = ctx->devs[0];

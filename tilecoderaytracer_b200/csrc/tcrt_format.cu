@@ -301,3 +301,24 @@ cudaError_t tcrt_launch_fp32_peak(bool fma, float* scratch, int grid, int iters,
     else fp32_peak_kernel<false><<<grid, 256, 0, stream>>>(scratch, iters, 0.999f, 1e-3f);
     return cudaGetLastError();
 }
+
+// ---- 8-bit quantisation for the image outputs (tcrt_write_ppm) ------------------------------------------
+// q(c) = floor(clamp(c, 0, 1) * 255 + 0.5) on the float promoted to double: the quantisation the
+// parity tolerance is stated in (last row).  NaN -> 0.  Layout stays x-major; the host
+// turns it into image rows while writing (6 MB at 1080p).
+namespace {
+__global__ void quantize8_kernel(const float* __restrict__ rgb, size_t n_values, unsigned char* __restrict__ out) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_values; i += (size_t)gridDim.x * blockDim.x) {
+        const double c = (double)rgb[i];
+        const double cl = c > 0.0 ? (c < 1.0 ? c : 1.0) : 0.0;   // NaN fails both compares -> 0
+        out[i] = (unsigned char)floor(cl * 255.0 + 0.5);
+    }
+}
+}  // namespace
+
+cudaError_t tcrt_launch_quantize8(const float* rgb, size_t n_values, unsigned char* out, cudaStream_t stream) {
+    if (n_values == 0) return cudaSuccess;
+    const int grid = (int)min((n_values + 255) / 256, (size_t)148 * 16);
+    quantize8_kernel<<<grid, 256, 0, stream>>>(rgb, n_values, out);
+    return cudaGetLastError();
+}
