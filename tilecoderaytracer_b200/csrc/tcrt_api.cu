@@ -47,6 +47,11 @@ struct DeviceState {
     unsigned long long* h_txt = nullptr;      // pinned: [0] flag, [1] total bytes
     bool txt_fixed = true;
     size_t txt_bytes = 0;
+    // row order of the current launch (most expensive rows first)
+    int* row_order = nullptr;
+    size_t row_order_cap = 0;
+    unsigned long long row_order_serial = 0;
+    int row_order_h = 0;
     // L2 flush scratch
     void* flush = nullptr;
     size_t flush_bytes = 0;
@@ -66,6 +71,11 @@ struct tcrt_ctx {
     std::vector<int> cut;
     tcrt_params cut_params{};
     bool cut_valid = false;
+    // per-column cost estimate of the last tcrt_balance_columns (low resolution), for the same key
+    std::vector<double> col_costs, row_costs;
+    tcrt_params cost_params{};
+    bool costs_valid = false;
+    unsigned long long cost_serial = 0;    // bumped by every new cost map
     char* host_text = nullptr;   // pinned staging for tcrt_write_txt
     size_t host_text_cap = 0;
 };
@@ -116,6 +126,7 @@ void free_device(DeviceState& d) {
     cudaFree(d.block_sums);
     cudaFree(d.flag);
     cudaFree(d.flush);
+    cudaFree(d.row_order);
     cudaFreeHost(d.h_counters);
     cudaFreeHost(d.h_txt);
     if (d.ev_k0) cudaEventDestroy(d.ev_k0);
@@ -568,6 +579,7 @@ int tcrt_upload_scene(tcrt_ctx* ctx, const tcrt_scene* s, const tcrt_camera* cam
     }
     ctx->cam = *cam;
     ctx->cut_valid = false;
+    ctx->costs_valid = false;
     ctx->has_scene = true;
     ctx->has_frame = false;
     ctx->txt_prepared = false;
@@ -734,6 +746,28 @@ static int launch_band(tcrt_ctx* ctx, DeviceState& d, const tcrt_params* p, int 
     rl.queue = reinterpret_cast<unsigned int*>(d.ctl);
     rl.counters = reinterpret_cast<unsigned long long*>(d.ctl + 8);
     rl.col_cost = col_cost;
+    // Longest-processing-time-first: with a cost map for this (scene, camera, params) — i.e. after
+    // tcrt_balance_columns — the queue runs row by row, the expensive rows first, so the tail of the
+    // launch is made of cheap pixels (sky, floor) instead of the deepest reflection paths, whose
+    // bounces are sequential and would otherwise drain on an almost empty GPU.
+    rl.row_order = nullptr;
+    const tcrt_params& cp = ctx->cost_params;
+    if (ctx->costs_valid && !col_cost && p->height > 1 && cp.width == p->width && cp.height == p->height &&
+        cp.max_depth == p->max_depth && cp.shadows_on == p->shadows_on && cp.reflections_on == p->reflections_on) {
+        if (d.row_order_serial != ctx->cost_serial || d.row_order_h != p->height || !d.row_order) {
+            const int n = p->height, nl = (int)ctx->row_costs.size();
+            std::vector<int> order(n);
+            for (int i = 0; i < n; i++) order[i] = i;
+            auto cost_of = [&](int z) { return ctx->row_costs[std::min(nl - 1, (int)((long long)z * nl / n))]; };
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost_of(a) > cost_of(b); });
+            int rc = ensure(ctx, d.row_order, d.row_order_cap, (size_t)n);
+            if (rc) return rc;
+            CK(ctx, cudaMemcpyAsync(d.row_order, order.data(), sizeof(int) * n, cudaMemcpyHostToDevice, d.stream));
+            d.row_order_serial = ctx->cost_serial;
+            d.row_order_h = n;
+        }
+        rl.row_order = d.row_order;
+    }
     CK(ctx, tcrt_launch_render(rl, d.sm_count, d.stream, launches));
     return TCRT_OK;
 }
@@ -818,21 +852,27 @@ int tcrt_balance_columns(tcrt_ctx* ctx, const tcrt_params* p, int n_bands, int* 
     d.x1 = lp.width;
     d.height = lp.height;
     unsigned int* col_cost = nullptr;
-    CK(ctx, cudaMalloc((void**)&col_cost, sizeof(unsigned int) * lp.width));
-    std::vector<unsigned int> h(lp.width);
+    const size_t n_cost = (size_t)lp.width + lp.height;    // per column, then per row
+    CK(ctx, cudaMalloc((void**)&col_cost, sizeof(unsigned int) * n_cost));
+    std::vector<unsigned int> h(n_cost);
     int launches = 0;
     int rc = TCRT_OK;
-    cudaError_t e = cudaMemsetAsync(col_cost, 0, sizeof(unsigned int) * lp.width, d.stream);
+    cudaError_t e = cudaMemsetAsync(col_cost, 0, sizeof(unsigned int) * n_cost, d.stream);
     if (e == cudaSuccess) rc = ensure(ctx, d.frame, d.frame_cap, (size_t)lp.width * lp.height * 3);
     if (e == cudaSuccess && rc == TCRT_OK) e = cudaMemsetAsync(d.ctl, 0, 64, d.stream);
     if (e == cudaSuccess && rc == TCRT_OK) rc = launch_band(ctx, d, &lp, 0, lp.width, col_cost, &launches);
     if (e == cudaSuccess && rc == TCRT_OK)
-        e = cudaMemcpyAsync(h.data(), col_cost, sizeof(unsigned int) * lp.width, cudaMemcpyDeviceToHost, d.stream);
+        e = cudaMemcpyAsync(h.data(), col_cost, sizeof(unsigned int) * n_cost, cudaMemcpyDeviceToHost, d.stream);
     if (e == cudaSuccess && rc == TCRT_OK) e = cudaStreamSynchronize(d.stream);
     cudaFree(col_cost);
     if (rc) return rc;
     if (e != cudaSuccess) return fail(ctx, TCRT_ERR_CUDA, "balance pre-pass failed: %s", cudaGetErrorString(e));
-    std::vector<double> costs(h.begin(), h.end());
+    std::vector<double> costs(h.begin(), h.begin() + lp.width);
+    ctx->col_costs = costs;
+    ctx->row_costs.assign(h.begin() + lp.width, h.end());
+    ctx->cost_params = *p;
+    ctx->costs_valid = true;
+    ctx->cost_serial++;
     if (tcrt_bands_from_costs(costs.data(), lp.width, p->width, n_bands, bounds) != TCRT_OK)
         return fail(ctx, TCRT_ERR_INVALID, "bands_from_costs failed");
     return TCRT_OK;
@@ -899,6 +939,7 @@ int tcrt_set_camera(tcrt_ctx* ctx, const tcrt_camera* cam) {
     if (!ctx->has_scene) return fail(ctx, TCRT_ERR_NO_SCENE, "tcrt_upload_scene has not been called");
     ctx->cam = *cam;
     ctx->cut_valid = false;
+    ctx->costs_valid = false;
     return TCRT_OK;
 }
 
