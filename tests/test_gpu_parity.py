@@ -74,6 +74,28 @@ def test_axis_aligned_box_scenes_bit_exact(gpu_ctx, seed, n):
     check_counters(stats, cnt)
 
 
+@pytest.mark.parametrize("scene_name", ["default", "boxes:3:14", "boxes:7:9", "two_mirrors"])
+def test_axis_parallel_rays(gpu_ctx, scene_name):
+    """A camera looking straight down +y with an axis-aligned screen: the centre column has D.x == 0
+    and the centre row D.z == 0 exactly, and every mirror bounce off an axis-aligned face keeps such
+    components zero.  Those rays bypass the box clusters' reciprocal (clu_wild) and hit den == 0 in the
+    plane tests (SceneFinitePlane.cpp:96-97)."""
+    scene, cam = make_scene(scene_name)
+    c = cam.export()
+    eye = (0.37, -6.2, 1.3)
+    for k in range(3):
+        c.eye[k] = eye[k]
+        c.screen_origin[k] = eye[k] + (1.0 if k == 1 else 0.0)
+        c.horizontal[k] = 1.0 if k == 0 else 0.0
+        c.vertical[k] = 1.0 if k == 2 else 0.0
+    p = api.default_params(96, 64, 12)
+    gpu_ctx.upload_flat(scene.flatten(), c)
+    img, stats = gpu_ctx.render(p)
+    want, cnt = O.render(scene.flatten(), c, p)
+    assert_bit_identical(img, want, f"{scene_name} axis-parallel camera")
+    check_counters(stats, cnt)
+
+
 def test_shared_reciprocal_division_is_ieee(gpu_ctx):
     """vector3d::normalize divides three components by one length (vector3d.h:57-74); the kernel
     shares the reciprocal between the three IEEE quotients.  2^31 random operand triples (zeros,
