@@ -383,7 +383,11 @@ def run_ours(args):
         achieved = flops_per_launch / kernel_s / 1e12
         line["roofline"] = {
             "bound": "fp32_pipe", "achieved": achieved, "peak": peak["unfused_tera_inst"], "unit": "TFLOP/s",
-            "frac": achieved / peak["unfused_tera_inst"], "traffic": None,
+            "frac": achieved / peak["unfused_tera_inst"], "traffic": ncu_traffic(args.workload),
+            "traffic_what": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, bytes, from the committed "
+                            "ncu --set full capture of this workload (profiles/ncu_metrics_r1.json); the frame "
+                            "(12 B/pixel) mostly stays in the 126 MB L2 during the launch",
+
             "kernel": "render_kernel", "kernel_ms": 1e3 * kernel_s,
             "algorithmic_flops_per_ray": flops_per_ray, "algorithmic_flops_per_launch": flops_per_launch,
             "peak_source": "measured live: tcrt_fp32_peak, dependent FMUL+FADD chains (1 flop per lane-instruction; "
@@ -399,6 +403,13 @@ def run_ours(args):
     ctx.close()
     D.shutdown()
     return 0
+
+
+def ncu_traffic(workload):
+    try:
+        return float(json.load(open(os.path.join(ROOT, "profiles", "ncu_metrics_r1.json")))[workload]["dram_bytes_per_launch"])
+    except Exception:
+        return None
 
 
 def measured_hbm_gbs():
