@@ -461,9 +461,10 @@ int tcrt_upload_scene(tcrt_ctx* ctx, const tcrt_scene* s, const tcrt_camera* cam
     ds.idx_off = ds.cslot_off + (6 * ds.n_clu + 3) / 4;
     const int n_prims = ds.n_sph + ds.n_fin + ds.n_inf;
     ds.blob_f4 = ds.idx_off + (n_prims + 3) / 4;
-    if ((size_t)ds.blob_f4 * sizeof(float4) > tcrt_render_max_smem())
+    ds.stage_off = ds.n_sph_bvh;   // BVH leaves read their spheres through L1
+    if ((size_t)(ds.blob_f4 - ds.stage_off) * sizeof(float4) > tcrt_render_max_smem())
         return fail(ctx, TCRT_ERR_UNSUPPORTED, "scene needs %zu B of shared memory per CTA (limit %zu)",
-                    (size_t)ds.blob_f4 * sizeof(float4), tcrt_render_max_smem());
+                    (size_t)(ds.blob_f4 - ds.stage_off) * sizeof(float4), tcrt_render_max_smem());
 
     const size_t off_surface = (size_t)ds.blob_f4;
     const size_t off_material = off_surface + n;

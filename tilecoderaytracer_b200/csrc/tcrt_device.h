@@ -28,6 +28,8 @@
 struct DeviceScene {
     const float4* blob;        // sweep blob (global)
     int blob_f4;               // size in float4 units (including the index tail, rounded up)
+    int stage_off;             // CTAs stage blob[stage_off, blob_f4) into shared memory: the spheres a BVH covers
+                               // (the first n_sph_bvh) are read from global memory through L1
     int n_sph, n_fin, n_inf;
     int n_sph_nl, n_fin_nl, n_inf_nl;   // non-light prefix lengths
     int n_sph_bvh, n_fin_bvh;           // BVH-covered prefix of the non-light prefix (0 = none)
