@@ -410,6 +410,11 @@ int tcrt_upload_scene(tcrt_ctx* ctx, const tcrt_scene* s, const tcrt_camera* cam
         if (bvh_f.empty() && ds.n_fin_nl > 0) {
             std::vector<int> cand(pf.begin(), pf.begin() + ds.n_fin_nl), is_arect;
             tcrt_build_box_clusters(s->fin_geom, cand, is_arect, clusters);
+            // a handful of rectangles is swept one by one: the cluster code would only cost
+            // instruction-cache space (the reference's SCENE 2 has four finite planes)
+            int n_rect = 0;
+            for (int a : is_arect) n_rect += a != 0;
+            if (n_rect < 6) clusters.clear();
             if (!clusters.empty()) {
                 std::vector<int> np, new_pos(ds.n_fin_nl, -1);
                 for (int k = 0; k < ds.n_fin_nl; k++)
