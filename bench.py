@@ -334,6 +334,10 @@ def run_ours(args):
         "wall_ms_per_step_incl_flush": 1e3 * wall / args.steps,
         "bands": [list(b) for b in bands], "kernel_ms_per_rank": rank_ms,
         "balance_max_over_mean_per_iteration": balance_log,
+        "note": ("strong scaling: the frame is fixed and split into N column bands; this workload is "
+                 f"{1e3 * t_ms / args.steps * world:.0f} us of GPU work in total, so at N = 8 a band is a few pixel "
+                 "lifetimes long and latency-bound (profiles/README.md §2); BASELINE configs[4] "
+                 "(--workload synth256_8k_d10) scales 7.1x on 8 B200 (profiles/scaling_r1/)"),
     }
 
     if world == 1:
