@@ -340,6 +340,7 @@ int tcrt_upload_scene(tcrt_ctx* ctx, const tcrt_scene* s, const tcrt_camera* cam
     // type's array is re-ordered into leaf order.  `n_*_nl` keeps meaning "non-light" (the shadow
     // sweep's range); `n_*_bvh` <= n_*_nl is the BVH-covered prefix, the rest is swept linearly.
     std::vector<float4> bvh_s, bvh_f;
+    int bvh_depth_s = 0, bvh_depth_f = 0;
     std::vector<TcrtBoxCluster> clusters;
     ds.n_fin_gen = ds.n_fin_nl;
     ds.n_arect = 0;
@@ -384,7 +385,7 @@ int tcrt_upload_scene(tcrt_ctx* ctx, const tcrt_scene* s, const tcrt_camera* cam
                 grow(&boxes_s[6 * k]);
                 rmin = std::min(rmin, sqrtf(s->sphere_geom[4 * in[k] + 3]));
             }
-            ds.bvh_sph_root = tcrt_build_bvh(boxes_s, nb, ord, bvh_s);
+            ds.bvh_sph_root = tcrt_build_bvh(boxes_s, nb, ord, bvh_s, &bvh_depth_s);
             std::vector<int> np;
             for (int k = 0; k < nb; k++) np.push_back(in[ord[k]]);
             np.insert(np.end(), out.begin(), out.end());
@@ -399,7 +400,7 @@ int tcrt_upload_scene(tcrt_ctx* ctx, const tcrt_scene* s, const tcrt_camera* cam
                 fin_box(s->fin_geom + 16 * pf[k], margin, &boxes_f[6 * k]);
                 grow(&boxes_f[6 * k]);
             }
-            ds.bvh_fin_root = tcrt_build_bvh(boxes_f, ds.n_fin_nl, ord, bvh_f);
+            ds.bvh_fin_root = tcrt_build_bvh(boxes_f, ds.n_fin_nl, ord, bvh_f, &bvh_depth_f);
             std::vector<int> np(pf);
             for (int k = 0; k < ds.n_fin_nl; k++) np[k] = pf[ord[k]];
             pf.swap(np);
@@ -466,6 +467,8 @@ int tcrt_upload_scene(tcrt_ctx* ctx, const tcrt_scene* s, const tcrt_camera* cam
     ds.idx_off = ds.cslot_off + (6 * ds.n_clu + 3) / 4;
     const int n_prims = ds.n_sph + ds.n_fin + ds.n_inf;
     ds.blob_f4 = ds.idx_off + (n_prims + 3) / 4;
+    if (std::max(bvh_depth_s, bvh_depth_f) + 2 > TCRT_BVH_STACK)   // cannot happen below ~2^40 primitives (tcrt_bvh.cpp)
+        return fail(ctx, TCRT_ERR_UNSUPPORTED, "BVH depth %d exceeds the traversal stack", std::max(bvh_depth_s, bvh_depth_f));
     ds.stage_off = ds.n_sph_bvh;   // BVH leaves read their spheres through L1
     if ((size_t)(ds.blob_f4 - ds.stage_off) * sizeof(float4) > tcrt_render_max_smem())
         return fail(ctx, TCRT_ERR_UNSUPPORTED, "scene needs %zu B of shared memory per CTA (limit %zu)",

@@ -41,6 +41,7 @@ struct Builder {
     std::vector<int>& order;       // permuted in place
     std::vector<float4>& nodes;
     std::vector<double> suffix;
+    int max_depth = 0;
     int max_leaf = 4;   // 4 and 6 measure the same, 1-3 slower (profiles/README.md)
 
     Builder(const float* b, std::vector<int>& o, std::vector<float4>& n) : boxes(b), order(o), nodes(n) {}
@@ -60,6 +61,7 @@ struct Builder {
 
     // returns the encoded reference of the subtree over order[first, first+count)
     int build(int first, int count, int depth) {
+        max_depth = std::max(max_depth, depth);
         if (count <= max_leaf) return leaf_ref(first, count);
         const Box parent = bounds(first, count);
         int best_axis = -1, best_split = -1;
@@ -121,10 +123,12 @@ struct Builder {
 
 }  // namespace
 
-int tcrt_build_bvh(const std::vector<float>& boxes, int n, std::vector<int>& order, std::vector<float4>& nodes) {
+int tcrt_build_bvh(const std::vector<float>& boxes, int n, std::vector<int>& order, std::vector<float4>& nodes, int* depth) {
     order.resize(n);
     for (int i = 0; i < n; i++) order[i] = i;
     nodes.clear();
     Builder b(boxes.data(), order, nodes);
-    return b.build(0, n, 0);
+    const int root = b.build(0, n, 0);
+    if (depth) *depth = b.max_depth;
+    return root;
 }

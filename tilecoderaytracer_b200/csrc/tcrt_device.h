@@ -62,7 +62,9 @@ struct DeviceScene {
 // and the function value is the encoded root reference.
 #ifdef __cplusplus
 #include <vector>
-int tcrt_build_bvh(const std::vector<float>& boxes, int n, std::vector<int>& order, std::vector<float4>& nodes);
+int tcrt_build_bvh(const std::vector<float>& boxes, int n, std::vector<int>& order, std::vector<float4>& nodes,
+                   int* depth);   // *depth: deepest node; the kernel's traversal stack holds TCRT_BVH_STACK entries
+#define TCRT_BVH_STACK 48
 #endif
 
 struct RenderLaunch {
