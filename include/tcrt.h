@@ -186,7 +186,8 @@ int tcrt_device_frame(tcrt_ctx* ctx, int device_slot, void** dev_ptr, size_t* n_
  * it before the timed region); a multi-device ctx computes it once per (scene, params). */
 int tcrt_balance_columns(tcrt_ctx* ctx, const tcrt_params* params, int n_bands, int* bounds);
 /* The cut itself (host only, no device needed): costs[i] >= 0 for n_costs equal-width column groups
- * covering [0, width). */
+ * covering [0, width).  When width is a multiple of 4 (and bands are at least 16 columns wide on
+ * average) so is every cut: the kernel's pixel tiles are 4 columns wide. */
 int tcrt_bands_from_costs(const double* costs, int n_costs, int width, int n_bands, int* bounds);
 
 /* Feedback step (host only): given the kernel time ms[b] of every band of the cut `bounds`, the cut

@@ -764,17 +764,26 @@ static int launch_band(tcrt_ctx* ctx, DeviceState& d, const tcrt_params* p, int 
     const tcrt_params& cp = ctx->cost_params;
     if (ctx->costs_valid && !col_cost && p->height > 1 && cp.width == p->width && cp.height == p->height &&
         cp.max_depth == p->max_depth && cp.shadows_on == p->shadows_on && cp.reflections_on == p->reflections_on) {
-        if (d.row_order_serial != ctx->cost_serial || d.row_order_h != p->height || !d.row_order) {
-            const int n = p->height, nl = (int)ctx->row_costs.size();
+        // rows, or 8-row tile rows when the launch is tiled (same rule as tcrt_launch_render)
+        const bool tiled = (cx1 - cx0) % 4 == 0 && p->height % 8 == 0;
+        const int unit = tiled ? 8 : 1;
+        const int key_h = tiled ? -p->height : p->height;
+        if (d.row_order_serial != ctx->cost_serial || d.row_order_h != key_h || !d.row_order) {
+            const int n = p->height / unit, nl = (int)ctx->row_costs.size();
             std::vector<int> order(n);
             for (int i = 0; i < n; i++) order[i] = i;
-            auto cost_of = [&](int z) { return ctx->row_costs[std::min(nl - 1, (int)((long long)z * nl / n))]; };
+            auto cost_of = [&](int r) {
+                double c = 0.0;
+                for (int k = 0; k < unit; k++)
+                    c += ctx->row_costs[std::min(nl - 1, (int)((long long)(r * unit + k) * nl / p->height))];
+                return c;
+            };
             std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost_of(a) > cost_of(b); });
             int rc = ensure(ctx, d.row_order, d.row_order_cap, (size_t)n);
             if (rc) return rc;
             CK(ctx, cudaMemcpyAsync(d.row_order, order.data(), sizeof(int) * n, cudaMemcpyHostToDevice, d.stream));
             d.row_order_serial = ctx->cost_serial;
-            d.row_order_h = n;
+            d.row_order_h = key_h;
         }
         rl.row_order = d.row_order;
     }
@@ -836,6 +845,12 @@ int tcrt_bands_from_costs(const double* costs, int n_costs, int width, int n_ban
         }
         bounds[k] = std::min(width, std::max(bounds[k - 1], b));
     }
+    // The kernel hands out 4-column x 8-row tiles when a band's width is a multiple of 4
+    // (tcrt_render.cu): interior cuts move to the nearest multiple of 4 — two columns of imbalance
+    // at most — unless the bands are only a few columns wide.
+    if (width % 4 == 0 && width >= 16 * n_bands)
+        for (int k = 1; k < n_bands; k++)
+            bounds[k] = std::min(width, std::max(bounds[k - 1], ((bounds[k] + 2) / 4) * 4));
     return TCRT_OK;
 }
 

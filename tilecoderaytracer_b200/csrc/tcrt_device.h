@@ -79,11 +79,11 @@ struct RenderLaunch {
     float* out;              // (x1-x0)*height*3 floats, x-major
     unsigned int* queue;     // pixel queue head (zeroed before launch)
     unsigned long long* counters;   // [0] primary [1] shadow [2] reflect
-    const int* row_order;    // optional: permutation of the rows [0, height); the queue then runs row by row in this order
+    const int* row_order;    // optional: permutation of the rows [0, height) — of the 8-row tile rows [0, height/8) when
+                             // `tiled` — in which the queue runs
     unsigned int* col_cost;  // optional (balancer pre-pass): [x1-x0] per column then [height] per row, += bounces of every finished pixel
-    unsigned int chunk;      // most pixels a warp claims per atomic
-    unsigned int claim_div;  // a claim is at most (pixels left) / claim_div
     int refill_min;          // idle lanes a warp waits for before it takes new pixels (1..32)
+    int tiled;               // queue positions map to 4x8-pixel tiles (band width % 4 == 0, height % 8 == 0)
 };
 
 // host builder of the box clusters (tcrt_cluster.cpp).  Face f = 2*axis + k; an absent face has
