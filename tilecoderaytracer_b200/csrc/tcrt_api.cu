@@ -765,8 +765,8 @@ static int launch_band(tcrt_ctx* ctx, DeviceState& d, const tcrt_params* p, int 
     if (ctx->costs_valid && !col_cost && p->height > 1 && cp.width == p->width && cp.height == p->height &&
         cp.max_depth == p->max_depth && cp.shadows_on == p->shadows_on && cp.reflections_on == p->reflections_on) {
         // rows, or 8-row tile rows when the launch is tiled (same rule as tcrt_launch_render)
-        const bool tiled = (cx1 - cx0) % 4 == 0 && p->height % 8 == 0;
-        const int unit = tiled ? 8 : 1;
+        const bool tiled = (cx1 - cx0) % TCRT_TILE_W == 0 && p->height % TCRT_TILE_H == 0;
+        const int unit = tiled ? TCRT_TILE_H : 1;
         const int key_h = tiled ? -p->height : p->height;
         if (d.row_order_serial != ctx->cost_serial || d.row_order_h != key_h || !d.row_order) {
             const int n = p->height / unit, nl = (int)ctx->row_costs.size();
@@ -848,9 +848,9 @@ int tcrt_bands_from_costs(const double* costs, int n_costs, int width, int n_ban
     // The kernel hands out 4-column x 8-row tiles when a band's width is a multiple of 4
     // (tcrt_render.cu): interior cuts move to the nearest multiple of 4 — two columns of imbalance
     // at most — unless the bands are only a few columns wide.
-    if (width % 4 == 0 && width >= 16 * n_bands)
+    if (width % TCRT_TILE_W == 0 && width >= 4 * TCRT_TILE_W * n_bands)
         for (int k = 1; k < n_bands; k++)
-            bounds[k] = std::min(width, std::max(bounds[k - 1], ((bounds[k] + 2) / 4) * 4));
+            bounds[k] = std::min(width, std::max(bounds[k - 1], ((bounds[k] + TCRT_TILE_W / 2) / TCRT_TILE_W) * TCRT_TILE_W));
     return TCRT_OK;
 }
 

@@ -67,6 +67,12 @@ int tcrt_build_bvh(const std::vector<float>& boxes, int n, std::vector<int>& ord
 #define TCRT_BVH_STACK 48
 #endif
 
+// Pixel tile of one queue claim: TCRT_TILE_W columns x TCRT_TILE_H rows = 32 pixels, one per lane.
+#ifndef TCRT_TILE_W
+#define TCRT_TILE_W 4
+#endif
+#define TCRT_TILE_H (32 / TCRT_TILE_W)
+
 struct RenderLaunch {
     DeviceScene scene;
     tcrt_camera cam;
