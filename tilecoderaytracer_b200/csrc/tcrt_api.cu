@@ -670,8 +670,15 @@ static int render_impl(tcrt_ctx* ctx, const tcrt_params* p, int x0, int x1, floa
         }
         CK(ctx, cudaEventRecord(d.ev_k0, d.stream));
         for (int k = 0; k < n_chunks; k++) {
-            const int cx0 = d.x0 + (int)((long long)(d.x1 - d.x0) * k / n_chunks);
-            const int cx1 = d.x0 + (int)((long long)(d.x1 - d.x0) * (k + 1) / n_chunks);
+            // chunk boundaries on tile boundaries, so that every chunk of a tileable band is tileable
+            auto chunk_start = [&](int j) {
+                const int w = d.x1 - d.x0;
+                int c = (int)((long long)w * j / n_chunks);
+                if (j < n_chunks && w % TCRT_TILE_W == 0) c -= c % TCRT_TILE_W;
+                return d.x0 + c;
+            };
+            const int cx0 = chunk_start(k), cx1 = chunk_start(k + 1);
+            if (cx1 <= cx0) continue;
             if (k > 0) CK(ctx, cudaMemsetAsync(d.ctl, 0, 4, d.stream));   // queue head only; ray counters accumulate
             rc = launch_band(ctx, d, p, cx0, cx1, nullptr, &launches);
             if (rc) return rc;
