@@ -219,7 +219,9 @@ def oracle_sample_bands(scene_name, w, h, depth, bands, stride):
 def workload_config(name, n_gpus):
     scene, w, h, depth = WORKLOADS[name]
     return {"workload": name, "scene": scene, "width": w, "height": h, "max_depth": depth, "shadows": True,
-            "reflections": True, "partition": f"{n_gpus} cost-balanced column band(s), one per GPU, no collective",
+            "reflections": True, "partition": f"{n_gpus} cost-balanced column band(s), one per GPU, no collective"
+                         + ("" if int(os.environ.get("WORLD_SIZE", "1")) > 1 or n_gpus == 1 else
+                            " (one process, multi-device tcrt_ctx)"),
             "l2": "flushed between timed steps (the kernel reads no large input: scene lives in shared memory)"}
 
 
@@ -243,14 +245,20 @@ def run_ours(args):
     cam = api.Camera()
     scene = api.Scene().build(scene_name, cam)
     params = api.default_params(w, h, depth)
-    ctx = api.Context([local])
+    # --gpus N without torchrun: ONE process drives N GPUs through a multi-device tcrt_ctx (the
+    # library cuts, balances and stitches the bands itself); under torchrun: one rank per GPU.
+    inproc = world == 1 and args.gpus > 1
+    ctx = api.Context(list(range(args.gpus)) if inproc else [local])
     ctx.upload(scene, cam)
     # one column band per rank; the cut is cost-balanced (a low-resolution pre-pass on rank 0 that
-    # measures SM clocks per column, shared once at setup) and outside the timed region
+    # counts bounces per column, shared once at setup) and outside the timed region
     bands = ctx.balance_columns(params, world) if rank == 0 else None
     bands = D.broadcast_object(bands)
     x0, x1 = bands[rank]
     flat, camx = scene.flatten(), cam.export()
+    if inproc:
+        for _ in range(12):                   # the ctx re-cuts after every whole-frame render
+            ctx.render_device(params)
 
     # ---- at N > 1, feedback on the cut: every rank re-cuts from the same gathered band times (so all
     # agree) until the slowest band is within 1 % of the mean; the cut is then frozen -------------------
@@ -285,7 +293,7 @@ def run_ours(args):
         for _ in range(args.steps):
             ctx.flush_l2()
             st = ctx.render_device(params, x0, x1)
-            kernel_ms.append(st.render_ms[0])
+            kernel_ms.append(max(st.render_ms))       # in-process multi-device: the slowest device
             rays_rank = st.rays
             launches += st.gpu_launches
     wall = time.perf_counter() - wall0
@@ -295,6 +303,8 @@ def run_ours(args):
     t_rank_ms = sum(kernel_ms)
     t_ms = D.reduce_max(t_rank_ms, tdev)              # slowest rank, device time
     rank_ms = [t / args.steps for t in D.gather_floats(t_rank_ms, tdev)]
+    if inproc:
+        rank_ms, bands = list(st.render_ms), st.bands
     rays_total = D.reduce_sum(rays_rank, tdev)        # per frame
     launches_total = int(D.reduce_sum(launches, tdev))
     value = rays_total * args.steps / (t_ms * 1e-3) / 1e6
