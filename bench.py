@@ -62,7 +62,7 @@ class ClockSampler:
         0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting",
     }
 
-    def __init__(self, index: int, period_s: float = 0.01):
+    def __init__(self, index: int, period_s: float = 0.002):
         self.index, self.period = index, period_s
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
