@@ -62,6 +62,7 @@ def test_oracle_txt_md5_other_configs(golden, key):
     ("synth1024", 80, 64, 50), ("synth256", 80, 64, 10), ("two_mirrors", 48, 40, 50),
     ("random:11:60", 96, 80, 10), ("random:12:200", 64, 48, 6), ("random:13:15", 96, 80, 30),
     ("random:14:500", 48, 40, 4), ("boxes:1:6", 96, 80, 8), ("boxes:2:10", 80, 64, 20), ("boxes:5:0", 64, 48, 5),
+    ("boxes:11:9", 72, 56, 15), ("boxes:12:4", 72, 56, 50), ("random:15:90", 72, 56, 25), ("random:16:7", 72, 56, 50),
 ])
 def test_oracle_matches_reference_binary(scene, w, h, d):
     """The unmodified reference (calculatePixel & co. compiled from /root/reference/src)."""
