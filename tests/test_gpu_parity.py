@@ -105,6 +105,18 @@ def test_shared_reciprocal_division_is_ieee(gpu_ctx):
         assert gpu_ctx.selftest_div3(1 << 30, seed) == 0
 
 
+@pytest.mark.parametrize("scene,w,h,d", [
+    ("boxes:11:9", 136, 104, 15), ("boxes:12:4", 100, 60, 50), ("random:15:90", 136, 104, 25),
+    ("random:16:7", 97, 61, 50), ("synth1024", 136, 104, 3), ("synth256", 97, 61, 30),
+])
+def test_more_scenes_tiled_and_untiled_sizes(gpu_ctx, scene, w, h, d):
+    """Frame sizes that are (136x104) and are not (100x60, 97x61) multiples of the 4x8 pixel tile, deep and
+    shallow recursion caps."""
+    img, stats, want, cnt = gpu_and_oracle(gpu_ctx, scene, w, h, d)
+    assert_bit_identical(img, want, f"{scene} {w}x{h} d{d}")
+    check_counters(stats, cnt)
+
+
 def test_switches_shadows_reflections(gpu_ctx):
     for kw in ({"shadows": False}, {"reflections": False}, {"shadows": False, "reflections": False}):
         img, stats, want, cnt = gpu_and_oracle(gpu_ctx, "default", 120, 90, 7, **kw)
