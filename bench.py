@@ -18,6 +18,13 @@ copied back to its own pinned host buffer in the e2e leg.  Rank 0 prints ONE JSO
              lane-instruction rate measured live by tcrt_fp32_peak (unfused FMUL+FADD mix).
   cpu_baseline  the reference itself (oracle/_ref/ref_render: calculatePixel & co. compiled from
              the reference's sources) on the host cores, bounded sample; rank 0, N=1 only.
+  also       e2e_multiframe (scene resident, new camera per frame, frame to the host), e2e_txt
+             (render + GPU "%f" formatting + D2H + file write), bands / kernel_ms_per_rank /
+             balance_max_over_mean_per_iteration (the cost-balanced cut and how its feedback converged).
+
+At N > 1 the frame is split into cost-balanced column bands (tcrt_balance_columns on rank 0, shared
+once, refined from the gathered band times before the timed region).  Without torchrun, --gpus N
+drives N GPUs from one process through a multi-device tcrt_ctx instead.
 
 --impl reference times the reference on all host cores (one process per core, column bands —
 the reference's own strategy-1 partition), each step a bounded column sample of the workload.
