@@ -179,11 +179,12 @@ int tcrt_download(tcrt_ctx* ctx, float* host_rgb_band);
 int tcrt_device_frame(tcrt_ctx* ctx, int device_slot, void** dev_ptr, size_t* n_floats);
 /* Cost-balanced column bands (replaces the equal z-bands of the reference's strategy 1,
  * RayTracer.cpp:904-906, whose load imbalance strategies 2-7 and PixelQueue were written to fix).
- * Renders a low-resolution copy of the frame on device slot 0 while charging the SM clocks of every
- * bounce to the columns of the pixels alive in it, then cuts [0, width) into n_bands bands of equal estimated cost: bounds[0] = 0 <= bounds[1] <= ...
- * <= bounds[n_bands] = width.  The estimate is a measurement (clocks), so two calls may differ by a
- * column or two: a multi-process run computes the cut on one rank and shares it (bench.py broadcasts
- * it before the timed region); a multi-device ctx computes it once per (scene, params). */
+ * Renders a low-resolution copy of the frame on device slot 0 in which every finished pixel adds its
+ * bounce count (reflection levels traced + 1) to its column and its row, then cuts [0, width) into
+ * n_bands bands of equal estimated cost: bounds[0] = 0 <= bounds[1] <= ... <= bounds[n_bands] = width.
+ * The estimate is deterministic for a (scene, camera, params); bounce counts are a proxy for time, so a
+ * multi-process run computes the cut on one rank, shares it, and refines it from measured band times
+ * (tcrt_rebalance_columns); a multi-device ctx computes it once per (scene, params). */
 int tcrt_balance_columns(tcrt_ctx* ctx, const tcrt_params* params, int n_bands, int* bounds);
 /* The cut itself (host only, no device needed): costs[i] >= 0 for n_costs equal-width column groups
  * covering [0, width).  When width is a multiple of 4 (and bands are at least 16 columns wide on

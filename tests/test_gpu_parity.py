@@ -468,3 +468,70 @@ def test_cpp_host_program_is_a_drop_in(golden, tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     txt = (tmp_path / "raytracer_screen.txt").read_bytes()
     assert pixel_md5(txt) == golden["md5"]["two_mirrors_500x504_d50"]["pixel_md5"]
+
+
+# ---- round 2: the sphere BVH that collapses into one leaf, text scenes ---------------------------------
+
+def _render_vs_oracle(ctx, s, cam, w=112, h=80, d=8, what=""):
+    p = api.default_params(w, h, d)
+    ctx.upload(s, cam)
+    img, stats = ctx.render(p)
+    want, cnt = O.render(s.flatten(), cam.export(), p)
+    assert_bit_identical(img, want, what)
+    check_counters(stats, cnt)
+
+
+def _lights_and_ground(s):
+    s.addSphere((-2, -6, 12), .15).setAsLightSource(.75)
+    s.addSphere((8, 2, 10), .15).setAsLightSource(1.0)
+    s.addInfinitePlane((0, 0, 0), (0, 0, 1), (1, 0, 0)).setCheckerBoard((1, 1, 1), (0, 0, 0), 3, 3) \
+        .setReflectiveFactor(.5).setDiffuseFactor(.5)
+
+
+def test_sphere_bvh_collapsing_into_one_leaf(gpu_ctx):
+    """>= 24 non-light spheres ask for a BVH, but after the exclusions (16 tiny spheres stay linear) only
+    8 coincident ones are left and SAH keeps them in ONE leaf: there are no nodes, the kernel without a
+    sphere BVH runs and must stage and sweep all 24 (tcrt_upload_scene once sized shared memory as if
+    8 of them were BVH-covered)."""
+    cam = api.Camera()
+    s = api.Scene()
+    _lights_and_ground(s)
+    for k in range(16):
+        s.addSphere((-1.5 + .4 * (k % 4), -1.0 + .4 * (k // 4), .3 + .05 * k), .02 + .001 * k) \
+            .setColor(1, k / 16, 0).setReflectiveFactor(.3 if k % 3 == 0 else 0.0)
+    for k in range(8):
+        s.addSphere((0.5, 0.5, 1.0), 1.0).setColor(k / 8, 1 - k / 8, .5).setReflectiveFactor(.5 if k == 0 else 0.0)
+    _render_vs_oracle(gpu_ctx, s, cam, what="24 spheres: 16 tiny + 8 coincident")
+
+
+@pytest.mark.parametrize("n_zero,n_real", [(30, 3), (40, 0), (26, 6), (5, 30)])
+def test_zero_radius_spheres(gpu_ctx, n_zero, n_real):
+    """Zero-radius spheres never enter the BVH (they would make the per-ray fattening infinite); with few
+    real spheres left the tree is a single leaf or empty."""
+    cam = api.Camera()
+    s = api.Scene()
+    _lights_and_ground(s)
+    for k in range(n_zero):
+        s.addSphere((-2 + .13 * k, -1 + .07 * k, .5 + .02 * k), 0.0).setColor(1, 0, 1)
+    for k in range(n_real):
+        s.addSphere((-1 + .9 * (k % 6), .5 * (k // 6), .6 + .1 * (k % 3)), .45).setColor(.2, .3 + .1 * (k % 5), 1) \
+            .setReflectiveFactor(.6 if k % 2 else 0.0)
+    _render_vs_oracle(gpu_ctx, s, cam, what=f"{n_zero} zero-radius + {n_real} spheres")
+
+
+def test_text_scene_renders_like_the_oracle(gpu_ctx):
+    """scenes/default.scene through tcrt_hscene_load_text, rendered on the GPU, against the
+    oracle on the same flattened arrays AND against the built-in Scene::initialize() frame."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cam = api.Camera()
+    s = api.Scene().load_text(os.path.join(root, "scenes", "default.scene"), cam)
+    p = api.default_params(200, 152, 50)
+    gpu_ctx.upload(s, cam)
+    img, stats = gpu_ctx.render(p)
+    want, cnt = O.render(s.flatten(), cam.export(), p)
+    assert_bit_identical(img, want, "default.scene vs oracle")
+    check_counters(stats, cnt)
+    scene2, cam2 = make_scene("default")
+    gpu_ctx.upload(scene2, cam2)
+    img2, _ = gpu_ctx.render(p)
+    assert_bit_identical(img, img2, "default.scene vs Scene::initialize()")

@@ -52,6 +52,9 @@ struct DeviceState {
     size_t row_order_cap = 0;
     unsigned long long row_order_serial = 0;
     int row_order_h = 0;
+    // balancer pre-pass: bounce counts per column, then per row (tcrt_balance_columns)
+    unsigned int* col_cost = nullptr;
+    size_t col_cost_cap = 0;
     // L2 flush scratch
     void* flush = nullptr;
     size_t flush_bytes = 0;
@@ -127,6 +130,7 @@ void free_device(DeviceState& d) {
     cudaFree(d.flag);
     cudaFree(d.flush);
     cudaFree(d.row_order);
+    cudaFree(d.col_cost);
     cudaFreeHost(d.h_counters);
     cudaFreeHost(d.h_txt);
     if (d.ev_k0) cudaEventDestroy(d.ev_k0);
@@ -393,6 +397,15 @@ int tcrt_upload_scene(tcrt_ctx* ctx, const tcrt_scene* s, const tcrt_camera* cam
             ps.swap(np);
             ds.n_sph_bvh = nb;
             ds.bvh_rmin = rmin * 0.999f;
+            // The tree collapsed into one leaf (few spheres left after the exclusions, or SAH keeps
+            // <= 8 coincident ones together): there are no nodes, the kernel variant without a sphere
+            // BVH runs, and it stages and sweeps EVERY sphere — so none may count as BVH-covered.
+            if (bvh_s.empty()) {
+                ds.n_sph_bvh = 0;
+                ds.bvh_sph_root = 0;
+                ds.bvh_rmin = 1.f;
+                bvh_depth_s = 0;
+            }
         }
         if (ds.n_fin_nl >= kFinBvhMin) {
             boxes_f.resize(6 * (size_t)ds.n_fin_nl);
@@ -883,12 +896,12 @@ int tcrt_balance_columns(tcrt_ctx* ctx, const tcrt_params* p, int n_bands, int* 
     d.x0 = 0;
     d.x1 = lp.width;
     d.height = lp.height;
-    unsigned int* col_cost = nullptr;
     const size_t n_cost = (size_t)lp.width + lp.height;    // per column, then per row
-    CK(ctx, cudaMalloc((void**)&col_cost, sizeof(unsigned int) * n_cost));
+    int rc = ensure(ctx, d.col_cost, d.col_cost_cap, n_cost);
+    if (rc) return rc;
+    unsigned int* col_cost = d.col_cost;
     std::vector<unsigned int> h(n_cost);
     int launches = 0;
-    int rc = TCRT_OK;
     cudaError_t e = cudaMemsetAsync(col_cost, 0, sizeof(unsigned int) * n_cost, d.stream);
     if (e == cudaSuccess) rc = ensure(ctx, d.frame, d.frame_cap, (size_t)lp.width * lp.height * 3);
     if (e == cudaSuccess && rc == TCRT_OK) e = cudaMemsetAsync(d.ctl, 0, 64, d.stream);
@@ -896,7 +909,6 @@ int tcrt_balance_columns(tcrt_ctx* ctx, const tcrt_params* p, int n_bands, int* 
     if (e == cudaSuccess && rc == TCRT_OK)
         e = cudaMemcpyAsync(h.data(), col_cost, sizeof(unsigned int) * n_cost, cudaMemcpyDeviceToHost, d.stream);
     if (e == cudaSuccess && rc == TCRT_OK) e = cudaStreamSynchronize(d.stream);
-    cudaFree(col_cost);
     if (rc) return rc;
     if (e != cudaSuccess) return fail(ctx, TCRT_ERR_CUDA, "balance pre-pass failed: %s", cudaGetErrorString(e));
     std::vector<double> costs(h.begin(), h.begin() + lp.width);
