@@ -11,6 +11,10 @@
 #   oracle/_ref/rt_fixed     same + shim 4 (hitALightSource_Var initialised).
 #   oracle/_ref/ref_render   oracle/ref_harness.cpp around the same sources: run-time W, H,
 #                            recursion cap, scene; raw float32 output.  Shims 1-4.
+#   oracle/_ref/ref_count    ref_render + two counter increments (rays entering calculatePixel past its
+#                            recursion check, RayTracer.cpp:454-457; shadow rays entering inShade, :750).
+#                            Never timed: bench.py --impl reference uses it once to count the rays of the
+#                            pixel sample that the uninstrumented ref_render is then timed on.
 #
 # Shims — none changes the arithmetic of the path:
 #   1. fixed_class.h / fixed_func.h: an un-vendored third-party fixed-point library
@@ -80,5 +84,12 @@ sed -i -e 's/^#define MAX_RECURSION_LEVEL 50/extern int g_ref_max_depth;\n#defin
     "$TMP/rt_project_parameters.h"
 grep -q 'g_ref_max_depth' "$TMP/rt_project_parameters.h"
 g++ $CXXFLAGS -I"$TMP" -I"$HERE/../scenes" "$HERE/ref_harness.cpp" -o "$OUT/ref_render"
+
+# (c) the counting twin (identical pixels; tests compare its counters with the oracle's)
+sed -i -e 's|/\* Lots of Magic happens here\.|g_ref_rays[recursion_level == 0 ? 0 : 2]++; /* Lots of Magic happens here.|' \
+       -e 's|sdecimal32 dist_to_light = dir.length();|g_ref_rays[1]++; sdecimal32 dist_to_light = dir.length();|' \
+    "$TMP/RayTracer.cpp"
+grep -c 'g_ref_rays\[' "$TMP/RayTracer.cpp" | grep -qx 2
+g++ $CXXFLAGS -DTCRT_REF_COUNT -I"$TMP" -I"$HERE/../scenes" "$HERE/ref_harness.cpp" -o "$OUT/ref_count"
 
 echo "build_ref: built $(ls "$OUT" | tr '\n' ' ')" >&2

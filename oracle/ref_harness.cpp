@@ -23,6 +23,8 @@
 //   --stride s : render only columns x0, x0+s, x0+2s, ... (bounded CPU samples for bench.py)
 
 int g_ref_max_depth = 50;   // replaces the literal of rt_project_parameters.h:73
+// ref_count only (build_ref.sh (c)): [0] primary, [1] shadow, [2] reflection rays
+unsigned long long g_ref_rays[3] = {0, 0, 0};
 
 #define main tcrt_reference_main_unused
 #include "RayTracer.cpp"
@@ -128,8 +130,16 @@ int main(int argc, char** argv) {
     }
     double t3 = now_s();
     fprintf(stderr, "{\"scene\": \"%s\", \"objects\": %d, \"W\": %d, \"H\": %d, \"depth\": %d, \"x0\": %d, \"x1\": %d, "
-           "\"stride\": %d, \"pixels\": %zu, \"render_s\": %.6f, \"txt_s\": %.6f}\n",
+           "\"stride\": %d, \"pixels\": %zu, \"render_s\": %.6f, \"txt_s\": %.6f"
+#ifdef TCRT_REF_COUNT
+           ", \"rays_primary\": %llu, \"rays_shadow\": %llu, \"rays_reflect\": %llu"
+#endif
+           "}\n",
            scene_name, my_scene.getObjectCount(), W, H, g_ref_max_depth, x0, x1, stride, out.size() / 3, t1 - t0,
-           txt_path ? (t3 - t2) : 0.0);
+           txt_path ? (t3 - t2) : 0.0
+#ifdef TCRT_REF_COUNT
+           , g_ref_rays[0], g_ref_rays[1], g_ref_rays[2]
+#endif
+           );
     return 0;
 }

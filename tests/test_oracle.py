@@ -121,3 +121,48 @@ def test_oracle_empty_scene_is_null_color():
     img, cnt = O.render(scene.flatten(), cam.export(), api.default_params(8, 6, 3))
     assert np.all(img == np.float32(0.75))
     assert cnt["rays_shadow"] == 0 and cnt["rays_reflect"] == 0
+
+
+@needs_ref
+@pytest.mark.parametrize("scene,w,h,d,stride", [("default", 120, 96, 50, 1), ("default", 64, 36, 5, 3),
+                                                ("synth256", 80, 64, 10, 2), ("synth1024", 60, 48, 50, 1),
+                                                ("two_mirrors", 40, 32, 50, 1), ("random:12:200", 64, 48, 6, 5)])
+def test_reference_ray_counters_equal_the_oracles(scene, w, h, d, stride):
+    """oracle/_ref/ref_count = the reference + two counter increments (build_ref.sh (c)): its primary /
+    shadow / reflection ray counts — what bench.py --impl reference divides by its time — equal the
+    oracle's counters (which the GPU kernel's counters are tested against), and its pixels equal ref_render's."""
+    import json
+
+    with tempfile.TemporaryDirectory() as td:
+        f32 = os.path.join(td, "o.f32")
+        r = subprocess.run([os.path.join(O.REF_DIR, "ref_count"), scene, str(w), str(h), str(d), "0", str(w), f32,
+                            "--stride", str(stride)], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, cwd=td)
+        info = json.loads(r.stderr.decode().strip().splitlines()[-1])
+        got = np.fromfile(f32, dtype=np.float32).reshape(-1, h, 3)
+    s, cam = make_scene(scene)
+    want, cnt = O.render(s.flatten(), cam.export(), api.default_params(w, h, d), 0, w, stride)
+    assert_bit_identical(got, want, "ref_count pixels")
+    for k in ("rays_primary", "rays_shadow", "rays_reflect"):
+        assert info[k] == cnt[k], k
+
+
+def test_bench_golden_columns_equal_the_oracle():
+    """tests/golden/bench_columns.json (made by the reference, checked by bench.py at every N): a few columns
+    of every workload re-rendered by the oracle give the same md5 and the same ray counts."""
+    import hashlib
+    import json
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    g = json.load(open(os.path.join(root, "tests", "golden", "bench_columns.json")))["workloads"]
+    assert {"default_500x504_d50", "default_1080p_d5", "default_4k_d50", "synth1024_4k_d50", "synth256_8k_d10"} <= set(g)
+    for name, e in g.items():
+        s, cam = make_scene(e["scene"])
+        p = api.default_params(e["W"], e["H"], e["depth"])
+        for i in (0, len(e["columns"]) // 2):
+            c = e["columns"][i]
+            col, _ = O.render(s.flatten(), cam.export(), p, c, c + 1, 1)
+            assert hashlib.md5(col[0].tobytes()).hexdigest() == e["md5"][i], (name, c)
+        if e["H"] <= 1080:     # the whole sample: ray counters too
+            _, cnt = O.render(s.flatten(), cam.export(), p, e["x0"], e["W"], e["stride"])
+            assert (cnt["rays_primary"], cnt["rays_shadow"], cnt["rays_reflect"]) == \
+                   (e["rays_primary"], e["rays_shadow"], e["rays_reflect"]), name

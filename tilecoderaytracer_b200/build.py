@@ -33,7 +33,7 @@ NVCC_FLAGS = [
 CXX_FLAGS = ["-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-Wall"]
 INCLUDES = ["-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "scenes")]
 
-CUDA_SOURCES = ["tcrt_render.cu", "tcrt_format.cu", "tcrt_api.cu", "tcrt_bvh.cpp", "tcrt_cluster.cpp"]
+CUDA_SOURCES = ["tcrt_render.cu", "tcrt_render_pool.cu", "tcrt_format.cu", "tcrt_api.cu", "tcrt_bvh.cpp", "tcrt_cluster.cpp"]
 HOST_SOURCES = ["host_scene.cpp", "host_capi.cpp"]
 
 
@@ -54,7 +54,7 @@ def _deps() -> list[str]:
     deps = []
     for d in (CSRC, os.path.join(ROOT, "include"), os.path.join(ROOT, "scenes")):
         for f in os.listdir(d):
-            if f.endswith((".cu", ".cuh", ".cpp", ".h", ".hpp", ".inc")):
+            if f.endswith((".cu", ".cuh", ".cpp", ".h", ".hpp", ".inc")):  # .cuh: shared device helpers
                 deps.append(os.path.join(d, f))
     deps.append(os.path.abspath(__file__))
     return deps
@@ -100,11 +100,12 @@ def build_ref() -> bool:
     """Builds oracle/_ref from /root/reference when it is present; keeps a prebuilt one otherwise."""
     script = os.path.join(ROOT, "oracle", "build_ref.sh")
     ref_bin = os.path.join(ROOT, "oracle", "_ref", "ref_render")
+    cnt_bin = os.path.join(ROOT, "oracle", "_ref", "ref_count")
     have_ref = os.path.isdir(os.environ.get("TCRT_REFERENCE_DIR", "/root/reference"))
-    if have_ref and _stale(ref_bin, [script, os.path.join(ROOT, "oracle", "ref_harness.cpp"),
-                                     os.path.join(ROOT, "scenes", "scene_builders.inc")]):
+    srcs = [script, os.path.join(ROOT, "oracle", "ref_harness.cpp"), os.path.join(ROOT, "scenes", "scene_builders.inc")]
+    if have_ref and (_stale(ref_bin, srcs) or _stale(cnt_bin, srcs)):
         _run(["bash", script])
-    return os.path.exists(ref_bin)
+    return os.path.exists(ref_bin) and os.path.exists(cnt_bin)
 
 
 if __name__ == "__main__":
