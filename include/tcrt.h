@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define TCRT_ABI_VERSION 1
+#define TCRT_ABI_VERSION 2
 #define TCRT_MAX_DEVICES 16
 
 enum {
@@ -174,6 +174,15 @@ int tcrt_render_columns(tcrt_ctx* ctx, const tcrt_params* params, int x0, int x1
 /* Same, result left in device memory (no copy-back); tcrt_download fetches it later. */
 int tcrt_render_device(tcrt_ctx* ctx, const tcrt_params* params, int x0, int x1, tcrt_stats* stats);
 int tcrt_download(tcrt_ctx* ctx, float* host_rgb_band);
+/* Asynchronous frames (multi-frame mode): tcrt_render_async queues columns [x0,x1) of a frame — into
+ * host_rgb_band when it is not NULL, which should then be pinned (tcrt_alloc_host) — and returns at once with a
+ * ticket; tcrt_wait(ticket) returns when that frame (and its copy-back) is complete and fills stats.  Every
+ * device holds two frame buffers, so frame n+1 renders while frame n's band crosses the bus: at most two
+ * frames are in flight, and a third tcrt_render_async fails with TCRT_ERR_INVALID until one has been waited
+ * for.  tcrt_set_camera / tcrt_upload_scene between the calls apply to the frames queued after them.  The
+ * "last render" the synchronous calls refer to (tcrt_download, tcrt_write_*) is the last frame WAITED for. */
+int tcrt_render_async(tcrt_ctx* ctx, const tcrt_params* params, int x0, int x1, float* host_rgb_band, int* ticket);
+int tcrt_wait(tcrt_ctx* ctx, int ticket, tcrt_stats* stats);
 /* Device address of a device's band of the last render (for zero-copy consumers, e.g. a
  * torch tensor view); floats = (col_end-col_begin)*height*3. */
 int tcrt_device_frame(tcrt_ctx* ctx, int device_slot, void** dev_ptr, size_t* n_floats);
@@ -245,6 +254,14 @@ int tcrt_txt_header(const tcrt_params* params, double run_time_s, char* buf, siz
 /* Whole file: header + pixel lines of the last render (must have covered columns
  * [0,width)).  run_time_s feeds the Run_Time / us/pixel tags. */
 int tcrt_write_txt(tcrt_ctx* ctx, const tcrt_params* params, const char* path, double run_time_s);
+/* One file from several processes (one per GPU, each holding one band of columns): one process creates the
+ * file — header + room for width*height lines of 31 bytes, the length of every pixel line whose channels
+ * are in [0, 10) — and, after a barrier of the caller's, every process writes the lines of the band it last
+ * rendered at their place (x-major order makes a band one run of lines, so no band waits for another).
+ * TCRT_ERR_UNSUPPORTED if a line of the band is not 31 bytes: gather the bands and use tcrt_write_txt.
+ * run_time_s must be the same in all calls (it is part of the header, whose length positions the lines). */
+int tcrt_txt_create(const tcrt_params* params, const char* path, double run_time_s);
+int tcrt_write_txt_band(tcrt_ctx* ctx, const tcrt_params* params, const char* path, double run_time_s);
 
 #ifdef __cplusplus
 }

@@ -535,3 +535,112 @@ def test_text_scene_renders_like_the_oracle(gpu_ctx):
     gpu_ctx.upload(scene2, cam2)
     img2, _ = gpu_ctx.render(p)
     assert_bit_identical(img, img2, "default.scene vs Scene::initialize()")
+
+
+# ---- round 2: asynchronous frames, the pipelined writer, the scene cache -------------------------------------
+
+def test_async_frames_equal_synchronous_frames(gpu_ctx):
+    """tcrt_render_async / tcrt_wait: two frames in flight with different cameras, each into its own pinned
+    buffer, are the frames the synchronous call renders; a third submit is refused until one is waited for."""
+    import copy
+
+    scene, cam = make_scene("default")
+    p = api.default_params(320, 200, 12)
+    gpu_ctx.upload(scene, cam)
+    cams = []
+    for i in range(5):
+        c = copy.copy(cam.export())
+        c.eye[0] += 0.05 * i
+        cams.append(c)
+    want = []
+    for c in cams:
+        gpu_ctx.set_camera(c)
+        img, st = gpu_ctx.render(p)
+        want.append((img.copy(), st.rays))
+    bufs = [api.HostBuffer(320 * 200 * 12) for _ in range(2)]
+    outs = [b.array(np.float32, (320, 200, 3)) for b in bufs]
+    tickets = []
+    for i, c in enumerate(cams):
+        if len(tickets) == 2:
+            j, t = tickets.pop(0)
+            st = gpu_ctx.wait(t)
+            assert np.array_equal(bits(outs[j % 2]), bits(want[j][0])) and st.rays == want[j][1]
+        gpu_ctx.set_camera(c)
+        tickets.append((i, gpu_ctx.render_async(p, out=outs[i % 2])))
+    with pytest.raises(api.TcrtError):
+        gpu_ctx.render_async(p, out=outs[0])          # two already in flight
+    for j, t in tickets:
+        st = gpu_ctx.wait(t)
+        assert np.array_equal(bits(outs[j % 2]), bits(want[j][0])) and st.rays == want[j][1]
+    with pytest.raises(api.TcrtError):
+        gpu_ctx.wait(0)                                # nothing pending any more
+    # the frame last waited for is "the last render" of the synchronous calls
+    got = np.empty((320, 200, 3), np.float32)
+    gpu_ctx.download(got)
+    assert np.array_equal(bits(got), bits(want[-1][0]))
+    gpu_ctx.set_camera(cam.export())
+
+
+def test_writer_falls_back_to_the_general_layout(gpu_ctx, tmp_path):
+    """A light of intensity 12 seen directly gives channels >= 10: pixel lines longer than 31 bytes.  The
+    pipelined fixed-width writer must notice and produce the general layout: the file equals glibc's."""
+    cam = api.Camera()
+    s = api.Scene()
+    s.addSphere((-2, -2, 2.0), .8).setAsLightSource(12.0)
+    s.addInfinitePlane((0, 0, 0), (0, 0, 1), (1, 0, 0)).setCheckerBoard((1, 1, 1), (0, 0, 0), 3, 3)
+    s.addSphere((0, 0, 1), 1.0).setColor(1, 0, 0).setReflectiveFactor(.7)
+    p = api.default_params(160, 120, 6)
+    gpu_ctx.upload(s, cam)
+    img, _ = gpu_ctx.render(p)
+    assert img.max() >= 10.0
+    path = str(tmp_path / "raytracer_screen.txt")
+    gpu_ctx.write_txt(p, path, 0.5)
+    txt = open(path, "rb").read()
+    assert txt == api.txt_header(p, 0.5) + O.format_txt(img)
+    with pytest.raises(api.TcrtError) as e:
+        api.txt_create(p, path, 0.5)
+        gpu_ctx.write_txt_band(p, path, 0.5)
+    assert e.value.code == _ffi.TCRT_ERR_UNSUPPORTED
+
+
+def test_bands_written_into_one_file(gpu_ctx, tmp_path):
+    """tcrt_txt_create + tcrt_write_txt_band (what one rank per GPU does): bands written in any order give the
+    file tcrt_write_txt gives."""
+    scene, cam = make_scene("default")
+    p = api.default_params(640, 360, 8)
+    gpu_ctx.upload(scene, cam)
+    gpu_ctx.render_device(p)
+    whole = str(tmp_path / "whole.txt")
+    gpu_ctx.write_txt(p, whole, 1.25)
+    parts = str(tmp_path / "parts.txt")
+    api.txt_create(p, parts, 1.25)
+    for x0, x1 in reversed(column_bands(640, 5)):
+        gpu_ctx.render_device(p, x0, x1)
+        gpu_ctx.write_txt_band(p, parts, 1.25)
+    assert open(parts, "rb").read() == open(whole, "rb").read()
+    # a file that tcrt_txt_create did not make for these params is refused
+    with pytest.raises(api.TcrtError) as e:
+        gpu_ctx.write_txt_band(p, parts, 12345.0)      # longer header -> other size
+    assert e.value.code == _ffi.TCRT_ERR_INVALID
+
+
+def test_scene_cache_sees_every_change(gpu_ctx):
+    """tcrt_upload_scene skips the rebuild for a bit-identical scene; any change must rebuild."""
+    cam = api.Camera()
+    p = api.default_params(96, 72, 6)
+
+    def build(shift, color):
+        s = api.Scene()
+        _lights_and_ground(s)
+        for k in range(30):
+            s.addSphere((-1 + .5 * (k % 6) + shift, .5 * (k // 6), .6), .22).setColor(color, .5, 1 - color) \
+                .setReflectiveFactor(.5 if k % 2 else 0.0)
+        return s
+
+    for shift, color in [(0.0, .2), (0.0, .2), (0.25, .2), (0.25, .9), (0.0, .2)]:
+        s = build(shift, color)
+        gpu_ctx.upload(s, cam)
+        img, stats = gpu_ctx.render(p)
+        want, cnt = O.render(s.flatten(), cam.export(), p)
+        assert_bit_identical(img, want, f"shift {shift} color {color}")
+        check_counters(stats, cnt)

@@ -69,7 +69,7 @@ def test_no_gpu_means_loud_failure_not_fallback():
 
 def test_abi_version_and_default_params():
     lib = _ffi.load()
-    assert lib.tcrt_abi_version() == 1
+    assert lib.tcrt_abi_version() == 2
     p = api.default_params()
     # rt_project_parameters.h:65-66,73-74, RayTracer.h:52
     assert (p.width, p.height, p.max_depth, p.shadows_on, p.reflections_on) == (500, 504, 50, 1, 1)

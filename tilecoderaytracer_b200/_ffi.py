@@ -87,6 +87,8 @@ SIGNATURES = {
                                       C.POINTER(TcrtStats)]),
     "tcrt_render_device": (C.c_int, [C.c_void_p, C.POINTER(TcrtParams), C.c_int, C.c_int, C.POINTER(TcrtStats)]),
     "tcrt_download": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "tcrt_render_async": (C.c_int, [C.c_void_p, C.POINTER(TcrtParams), C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
+    "tcrt_wait": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(TcrtStats)]),
     "tcrt_device_frame": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "tcrt_flush_l2": (C.c_int, [C.c_void_p]),
     "tcrt_balance_columns": (C.c_int, [C.c_void_p, C.POINTER(TcrtParams), C.c_int, C.POINTER(C.c_int)]),
@@ -103,6 +105,8 @@ SIGNATURES = {
                                      C.POINTER(C.c_size_t)]),
     "tcrt_txt_header": (C.c_int, [C.POINTER(TcrtParams), C.c_double, C.c_char_p, C.c_size_t]),
     "tcrt_write_txt": (C.c_int, [C.c_void_p, C.POINTER(TcrtParams), C.c_char_p, C.c_double]),
+    "tcrt_txt_create": (C.c_int, [C.POINTER(TcrtParams), C.c_char_p, C.c_double]),
+    "tcrt_write_txt_band": (C.c_int, [C.c_void_p, C.POINTER(TcrtParams), C.c_char_p, C.c_double]),
     # tcrt_host.h
     "tcrt_hscene_new": (C.c_void_p, []),
     "tcrt_hscene_free": (None, [C.c_void_p]),

@@ -266,6 +266,22 @@ class Context:
         self._ck(self._lib.tcrt_render_device(self._h, C.byref(params), x0, x1, C.byref(st)))
         return RenderStats.from_c(st)
 
+    def render_async(self, params: TcrtParams, x0: int = 0, x1: Optional[int] = None, out: Optional[np.ndarray] = None) -> int:
+        """Queue columns [x0,x1) of a frame (into `out`, pinned host memory, when given) and return a ticket at
+        once; at most two frames are in flight.  wait(ticket) completes it."""
+        x1 = params.width if x1 is None else x1
+        if out is not None:
+            assert out.dtype == np.float32 and out.size == (x1 - x0) * params.height * 3 and out.flags["C_CONTIGUOUS"]
+        t = C.c_int(-1)
+        self._ck(self._lib.tcrt_render_async(self._h, C.byref(params), x0, x1,
+                                             out.ctypes.data_as(C.c_void_p) if out is not None else None, C.byref(t)))
+        return t.value
+
+    def wait(self, ticket: int) -> RenderStats:
+        st = TcrtStats()
+        self._ck(self._lib.tcrt_wait(self._h, ticket, C.byref(st)))
+        return RenderStats.from_c(st)
+
     def download(self, out: np.ndarray) -> np.ndarray:
         self._ck(self._lib.tcrt_download(self._h, out.ctypes.data_as(C.c_void_p)))
         return out
@@ -323,6 +339,11 @@ class Context:
     def write_txt(self, params: TcrtParams, path: str, run_time_s: float = 0.0) -> None:
         self._ck(self._lib.tcrt_write_txt(self._h, C.byref(params), path.encode(), run_time_s))
 
+    def write_txt_band(self, params: TcrtParams, path: str, run_time_s: float = 0.0) -> None:
+        """The last rendered band's pixel lines at their place in a file made by txt_create (one file from
+        several processes, one per GPU)."""
+        self._ck(self._lib.tcrt_write_txt_band(self._h, C.byref(params), path.encode(), run_time_s))
+
     def write_ppm(self, params: TcrtParams, path: str) -> None:
         """The last render as an 8-bit binary PPM (row 0 = top of the image)."""
         self._ck(self._lib.tcrt_write_ppm(self._h, C.byref(params), path.encode()))
@@ -342,6 +363,13 @@ def txt_header(params: TcrtParams, run_time_s: float) -> bytes:
     if n < 0:
         raise TcrtError(n, "header formatting failed")
     return buf.raw[:n]
+
+
+def txt_create(params: TcrtParams, path: str, run_time_s: float = 0.0) -> None:
+    """Create the .txt with its header and room for width*height 31-byte pixel lines (see write_txt_band)."""
+    rc = _ffi.load().tcrt_txt_create(C.byref(params), path.encode(), run_time_s)
+    if rc != 0:
+        raise TcrtError(rc, _ffi.load().tcrt_last_error(None).decode())
 
 
 def device_count() -> int:
