@@ -15,7 +15,8 @@ own pinned host buffer in the e2e leg.  Rank 0 prints ONE JSON line.
              stream around every launch (tcrt_stats.render_ms), L2 flushed between steps, max over ranks.
   e2e        the same metric through the C-ABI call a user makes with HOST buffers: every step re-uploads
              the flattened scene (H2D) and tcrt_render_columns() copies the finished band into pinned host
-             memory (D2H); wall clock around the calls, max over ranks.
+             memory (D2H); wall clock around the calls, max over ranks.  e2e_async: the same with two frames in
+             flight (tcrt_render_async / tcrt_wait).
   configs    the same two measurements (fewer steps) for ALL FIVE BASELINE configs at this N, each with
              frac_executed / frac_algorithmic and a parity verdict.
   parity     outside the timed region, at every N: every rank compares sampled columns of its finished band
@@ -439,11 +440,16 @@ def run_workload(ctx, dist, args, name, steps, warmup, inproc, sample_clocks=Fal
         res["clocks"] = clocks.summary()
 
     # ---- e2e: host buffers, H2D scene + D2H band inside the timed region ----------------------------------------
+    # `e2e`: every step re-sends the flattened scene (tcrt_upload_scene) and renders into pinned host memory with
+    # the blocking call (tcrt_render_columns), one frame at a time.  `e2e_async`: the call sequence of a user who
+    # streams frames — the frame is queued with tcrt_render_async into one of two pinned buffers and the previous
+    # frame is waited for (tcrt_wait) while this one renders.
     ex0, ex1 = (0, w) if inproc else (x0, x1)
     band_floats = (ex1 - ex0) * h * 3
-    own = host is None or host.nbytes < band_floats * 4
-    hb = api.HostBuffer(band_floats * 4) if own else host
-    out = hb.array(np.float32, (ex1 - ex0, h, 3))
+    if host is None or host[0].nbytes < band_floats * 4:
+        host = [api.HostBuffer(band_floats * 4) for _ in range(2)]
+    outs = [hb.array(np.float32, (ex1 - ex0, h, 3)) for hb in host]
+    out = outs[0]
     e2e_steps = max(3, min(steps, 30))
     for _ in range(2):
         ctx.upload_flat(flat, camx)
@@ -453,18 +459,60 @@ def run_workload(ctx, dist, args, name, steps, warmup, inproc, sample_clocks=Fal
     for _ in range(e2e_steps):
         ctx.upload_flat(flat, camx)
         ctx.render(params, ex0, ex1, out)
+    sync_s = dist.max(time.perf_counter() - t0)
+    dist.barrier()
+    t0 = time.perf_counter()
+    tickets = []
+    for i in range(e2e_steps):
+        ctx.upload_flat(flat, camx)
+        tickets.append(ctx.render_async(params, ex0, ex1, out=outs[i % 2]))
+        if len(tickets) == 2:
+            ctx.wait(tickets.pop(0))
+    for t in tickets:
+        ctx.wait(t)
     e2e_s = dist.max(time.perf_counter() - t0)
-    res["e2e"] = {"value": rays_total * e2e_steps / e2e_s / 1e6, "unit": "Mrays/s",
+    out = outs[(e2e_steps - 1) % 2]
+    res["e2e"] = {"value": rays_total * e2e_steps / sync_s / 1e6, "unit": "Mrays/s",
                   "h2d_bytes_per_step": int(scene_bytes(flat) + 64), "d2h_bytes_per_step": int(band_floats * 4 + 32),
-                  "frames_per_s": e2e_steps / e2e_s, "steps": e2e_steps,
-                  "what": "tcrt_upload_scene + tcrt_render_columns into pinned host memory, wall clock"}
+                  "frames_per_s": e2e_steps / sync_s, "steps": e2e_steps,
+                  "what": "per frame: tcrt_upload_scene + tcrt_render_columns (blocking) into pinned host memory, wall clock"}
+    res["e2e_async"] = {"value": rays_total * e2e_steps / e2e_s / 1e6, "unit": "Mrays/s", "frames_per_s": e2e_steps / e2e_s,
+                        "h2d_bytes_per_step": int(scene_bytes(flat) + 64), "d2h_bytes_per_step": int(band_floats * 4 + 32),
+                        "what": "per frame: tcrt_upload_scene + tcrt_render_async into one of two pinned host buffers, tcrt_wait for "
+                                "the previous frame (two frames in flight); wall clock over all frames incl. the last wait"}
+    if name in ("default_1080p_d5", args.workload) and not inproc:
+        # ---- multi-frame mode: scene resident, a new camera per frame, frame to the host ----------
+        import copy
+
+        n_mf = max(6, min(steps * 2, 60))
+        cams = []
+        for i in range(n_mf):
+            c = copy.copy(camx)
+            c.eye[0] = camx.eye[0] + 0.002 * i       # a slow dolly: every frame is a different image
+            cams.append(c)
+        dist.barrier()
+        t0 = time.perf_counter()
+        tickets = []
+        for i, c in enumerate(cams):
+            ctx.set_camera(c)
+            tickets.append(ctx.render_async(params, ex0, ex1, out=outs[i % 2]))
+            if len(tickets) == 2:
+                ctx.wait(tickets.pop(0))
+        for t in tickets:
+            ctx.wait(t)
+        mf_s = dist.max(time.perf_counter() - t0)
+        ctx.set_camera(camx)
+        res["e2e_multiframe"] = {"frames_per_s": n_mf / mf_s, "frames": n_mf,
+                                 "what": "tcrt_set_camera + tcrt_render_async into pinned host memory per frame, two frames in "
+                                         "flight; scene stays on the device"}
+        ctx.render(params, ex0, ex1, out)           # the frame the parity check below looks at
     # ---- parity of what the e2e leg left in host memory, against the reference's own columns ---------------------
     n, ok = check_columns(name, out, ex0, ex1)
     n_all, ok_all = int(dist.sum(n)), int(dist.sum(ok))
     res["parity"] = {"checked": n_all > 0, "ok": n_all > 0 and ok_all == n_all, "columns": n_all, "columns_equal": ok_all,
                      "against": "tests/golden/bench_columns.json: md5 of float32 columns rendered by the reference itself "
                                 "(oracle/_ref/ref_render); every rank checks the columns inside its own band"}
-    res["_ctx_state"] = (params, x0, x1, out, flat, camx, hb)
+    res["_ctx_state"] = (params, x0, x1, out, flat, camx, host)
     return res
 
 
@@ -507,16 +555,15 @@ def multi_device_check(world):
             ctx.render_device(params)
         img, st = ctx.render(params)
         n, ok = check_columns(name, img, 0, w)
-        out = {"devices": world, "workload": name, "bands": [list(b) for b in st.bands], "kernel_ms_per_device": st.render_ms,
+        # (no timings here: the other ranks' processes still hold contexts on their GPUs, which this process time-shares)
+        out = {"devices": world, "workload": name, "bands": [list(b) for b in st.bands],
                "columns": n, "columns_equal": ok, "ok": n > 0 and n == ok}
         try:
             want = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))["md5"]["default_3840x2160_d50"]
             with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as td:
                 path = os.path.join(td, "raytracer_screen.txt")
                 ctx.render_device(params)
-                t0 = time.perf_counter()
                 ctx.write_txt(params, path, 0.0)
-                out["txt_ms"] = 1e3 * (time.perf_counter() - t0)
                 md5 = hashlib.md5()
                 with open(path, "rb") as f:
                     data = f.read()
@@ -529,6 +576,85 @@ def multi_device_check(world):
         return out
     finally:
         ctx.close()
+
+
+def txt_leg(ctx, dist, name, frames=3):
+    """render + .txt file of the reference's format (RayTracer.cpp:1574-1626) in tmpfs, at this N.  One rank: the
+    whole frame through tcrt_write_txt.  N ranks: rank 0 creates the file (tcrt_txt_create), every rank renders its
+    band and writes its lines at their place (tcrt_write_txt_band) — no gather.  The md5 of the pixel lines is
+    compared with the reference program's where tests/golden/golden.json has one."""
+    from tilecoderaytracer_b200 import api
+
+    rank, world = dist.rank, dist.world
+    scene_name, w, h, depth = WORKLOADS[name]
+    cam = api.Camera()
+    scene = api.Scene().build(scene_name, cam)
+    params = api.default_params(w, h, depth)
+    ctx.upload(scene, cam)
+    bands = dist.bcast(ctx.balance_columns(params, world) if rank == 0 else None)
+    x0, x1 = bands[rank]
+    td = dist.bcast(tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) if rank == 0 else None)
+    path = os.path.join(td, "raytracer_screen.txt")
+    times = []
+    for i in range(frames + 1):
+        dist.host_barrier()
+        t0 = time.perf_counter()
+        if world == 1:
+            ctx.render_device(params)
+            ctx.write_txt(params, path, 0.0)
+        else:
+            if rank == 0:
+                api.txt_create(params, path, 0.0)
+            dist.host_barrier()
+            ctx.render_device(params, x0, x1)
+            ctx.write_txt_band(params, path, 0.0)
+        dist.host_barrier()
+        if i > 0:
+            times.append(time.perf_counter() - t0)
+    out = None
+    if rank == 0:
+        size = os.path.getsize(path)
+        s = statistics.mean(times)
+        out = {"workload": name, "frames_per_s": 1.0 / s, "ms_per_frame": 1e3 * s, "file_bytes": size, "gb_per_s": size / s / 1e9,
+               "what": "render + GPU %f formatting + D2H of text + copies into the file (tmpfs), pipelined in 7.9 MB chunks; "
+                       + ("tcrt_write_txt" if world == 1 else "tcrt_txt_create on rank 0 + tcrt_write_txt_band on every rank")}
+        key = {"default_4k_d50": "default_3840x2160_d50", "default_1080p_d5": "default_1920x1080_d5"}.get(name)
+        if key:
+            want = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))["md5"][key]
+            data = open(path, "rb").read()
+            body = data[data.index(b"("):]
+            out["md5_equals_reference_file"] = hashlib.md5(body).hexdigest() == want["pixel_md5"] and len(body) == want["pixel_bytes"]
+        os.unlink(path)
+        os.rmdir(td)
+    dist.host_barrier()
+    return out
+
+
+def file_copy_bound(nbytes, threads=8):
+    """What the file system allows: `threads` threads copying nbytes from memory into the mapping of a NEW file
+    in the same tmpfs (page allocation + copy), GB/s — the .txt leg cannot be faster than this plus the render."""
+    import numpy as np
+
+    d = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    src = np.ones(nbytes, dtype=np.uint8)
+    best = None
+    for _ in range(3):
+        with tempfile.NamedTemporaryFile(dir=d) as f:
+            t0 = time.perf_counter()
+            f.truncate(nbytes)
+            mm = np.memmap(f.name, dtype=np.uint8, mode="r+", shape=(nbytes,))
+            cuts = [nbytes * i // threads for i in range(threads + 1)]
+            ts = [threading.Thread(target=lambda a, b: mm.__setitem__(slice(a, b), src[a:b]), args=(cuts[i], cuts[i + 1]))
+                  for i in range(threads)]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
+            dt = time.perf_counter() - t0
+            del mm
+        best = dt if best is None else min(best, dt)
+    return {"bytes": nbytes, "threads": threads, "ms": 1e3 * best, "gb_per_s": nbytes / best / 1e9,
+            "what": "numpy slices copied by threads into np.memmap of a new /dev/shm file (page faults + copy), best of 3"}
 
 
 # ---- the B200 arm -----------------------------------------------------------------------------------------
@@ -561,42 +687,9 @@ def run_ours(args):
                 "data path (torch.distributed carries only the barrier and the timing reductions)",
     }
 
-    if world == 1 and not inproc and not args.quick:
-        # ---- multi-frame mode: scene resident, a new camera per frame, frame to the host ----
-        import copy
-
-        n_mf = max(3, min(args.steps, 30))
-        cams = []
-        for i in range(n_mf):
-            c = copy.copy(camx)
-            c.eye[0] = camx.eye[0] + 0.002 * i       # a slow dolly: every frame is a different image
-            cams.append(c)
-        ctx.set_camera(cams[0])
-        ctx.render(params, x0, x1, out)
-        t0 = time.perf_counter()
-        for c in cams:
-            ctx.set_camera(c)
-            ctx.render(params, x0, x1, out)
-        mf_s = time.perf_counter() - t0
-        ctx.set_camera(camx)
-        line["e2e_multiframe"] = {"frames_per_s": n_mf / mf_s, "frames": n_mf,
-                                  "what": "tcrt_set_camera + tcrt_render_columns into pinned host memory per frame; "
-                                          "scene stays on the device"}
-        # ---- .txt writer leg (the reference's output format) -------------------------------------------------------
-        with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as td:
-            path = os.path.join(td, "raytracer_screen.txt")
-            ctx.render_device(params)
-            ctx.write_txt(params, path, 0.0)
-            n_txt = 3
-            t0 = time.perf_counter()
-            for _ in range(n_txt):
-                ctx.render_device(params)
-                ctx.write_txt(params, path, 0.0)
-            txt_s = (time.perf_counter() - t0) / n_txt
-            line["e2e_txt"] = {"frames_per_s": 1.0 / txt_s, "ms_per_frame": 1e3 * txt_s,
-                               "file_bytes": os.path.getsize(path),
-                               "what": "render + GPU %f formatting + D2H of text + file write (tmpfs)"}
-
+    if "e2e_multiframe" in head:
+        line["e2e_multiframe"] = head["e2e_multiframe"]
+    line["e2e_async"] = head["e2e_async"]
     # ---- all five BASELINE configs at this N ----------------------------------------------------------------------
     peak = ctx.fp32_peak() if rank == 0 else None
     results = {args.workload: head}
@@ -604,14 +697,25 @@ def run_ours(args):
         for name in BASELINE_CONFIGS:
             if name not in results:
                 r = run_workload(ctx, dist, args, name, max(3, min(args.steps, 10)), 3, inproc, host=hb)
+                if "e2e_multiframe" in r and name == "default_1080p_d5":
+                    line["e2e_multiframe_1080p"] = r["e2e_multiframe"]
                 r.pop("_ctx_state")
                 results[name] = r
+    if not args.quick and not inproc:
+        txt = {}
+        for name in dict.fromkeys(["default_4k_d50", args.workload]):
+            txt[name] = txt_leg(ctx, dist, name)
+        if rank == 0:
+            line["e2e_txt"] = txt[args.workload]
+            line["e2e_txt_4k"] = txt["default_4k_d50"]
+            line["file_copy_bound"] = file_copy_bound(txt["default_4k_d50"]["file_bytes"])
     if rank == 0:
         cfgs = {}
         for name, r in results.items():
             f = fractions(name, r, peak)
             cfgs[name] = {"ms": r["ms"], "mrays_s": r["mrays_s"], "frames_s": r["frames_s"], "steps": r["steps"],
                           "e2e": {k: r["e2e"][k] for k in ("value", "frames_per_s", "h2d_bytes_per_step", "d2h_bytes_per_step")},
+                          "e2e_async": {k: r["e2e_async"][k] for k in ("value", "frames_per_s")},
                           "frac_executed": f["frac_executed"], "frac_algorithmic": f["frac_algorithmic"],
                           "parity_ok": r["parity"]["ok"], "parity_columns": r["parity"]["columns"],
                           "bands": r["bands"], "kernel_ms_per_rank": r["kernel_ms_per_rank"]}
