@@ -362,3 +362,18 @@ def test_txt_to_ppm_tool(tmp_path):
     img = mod.to_image(mod.quant8(got))
     assert img.shape == (h, w, 3)
     assert tuple(img[1, 0]) == (255, 128, 0) and tuple(img[0, 2]) == (255, 64, 255)
+
+
+def test_txt_create_sizes_the_file_for_fixed_width_lines(tmp_path):
+    """tcrt_txt_create (host only): header + room for W*H pixel lines of 31 bytes, so that every rank of a
+    one-process-per-GPU run can write its band at its place (tcrt_write_txt_band) without a gather."""
+    p = api.default_params(40, 30, 5)
+    path = str(tmp_path / "raytracer_screen.txt")
+    api.txt_create(p, path, 1.5)
+    head = api.txt_header(p, 1.5)
+    data = open(path, "rb").read()
+    assert data.startswith(head) and len(data) == len(head) + 40 * 30 * 31
+    assert head.decode().splitlines()[7] == "Run_Time:1.500000."
+    with pytest.raises(api.TcrtError) as e:
+        api.txt_create(p, str(tmp_path / "no_such_dir" / "x.txt"), 0.0)
+    assert e.value.code == _ffi.TCRT_ERR_IO

@@ -117,6 +117,7 @@ struct tcrt_ctx {
     size_t scene_stage_cap = 0;     // float4s
     std::vector<unsigned char> scene_key;
     size_t scene_total_f4 = 0;
+    int n_objects = 0;
     DeviceScene scene_ds{};
     size_t scene_off[7] = {};       // surface, material, normals, frame, tex, bvh_s, bvh_f
     bool scene_bvh_s = false, scene_bvh_f = false;
@@ -606,10 +607,10 @@ static int build_scene_blob(tcrt_ctx* ctx, const tcrt_scene* s) {
         int* cslot = reinterpret_cast<int*>(&host[ds.cslot_off]);
         for (int c = 0; c < ds.n_clu; c++) {
             const TcrtBoxCluster& b = clusters[c];
-            host[ds.clu_off + 4 * c + 0] = make_float4(b.lo[0], b.lo[1], b.lo[2], b.hi[0]);
+            host[ds.clu_off + 4 * c + 0] = make_float4(b.lo[0], b.hi[0], b.lo[1], b.hi[1]);
             int present = 0;
             for (int f = 0; f < 6; f++) present |= (b.plane[f] >= 0) << f;
-            float4 b1 = make_float4(b.hi[1], b.hi[2], 0.f, 0.f);
+            float4 b1 = make_float4(b.lo[2], b.hi[2], 0.f, 0.f);
             memcpy(&b1.z, &present, 4);
             host[ds.clu_off + 4 * c + 1] = b1;
             host[ds.clu_off + 4 * c + 2] = make_float4(b.c[0], b.c[1], b.c[2], b.c[3]);
@@ -687,6 +688,7 @@ static int build_scene_blob(tcrt_ctx* ctx, const tcrt_scene* s) {
     }
     memcpy(ctx->scene_stage, host.data(), total_f4 * sizeof(float4));
     ctx->scene_total_f4 = total_f4;
+    ctx->n_objects = n;
     ctx->scene_ds = ds;
     ctx->scene_off[0] = off_surface;
     ctx->scene_off[1] = off_material;
@@ -940,6 +942,7 @@ static int launch_band(tcrt_ctx* ctx, DeviceState& d, const tcrt_params* p, int 
     rl.null_g = p->null_color[1];
     rl.null_b = p->null_color[2];
     rl.far_dist = p->far_dist;
+    rl.n_objects = ctx->n_objects;
     rl.out = d.fr().frame + (size_t)(cx0 - d.fr().x0) * p->height * 3;
     rl.queue = reinterpret_cast<unsigned int*>(d.fr().ctl);
     rl.counters = reinterpret_cast<unsigned long long*>(d.fr().ctl + 8);

@@ -18,7 +18,8 @@
 //   [inf_off, inf_off + n_inf)      infinite (n, -dto)
 //   [light_off, light_off + 2*n_lights)  (light position, intensity) (light colour, 0)
 //   [clu_off, clu_off + 4*n_clu)    box clusters of axis-aligned finite planes (tcrt_cluster.cpp):
-//                                   (lo.xyz, hi.x) (hi.yz, present mask, -) (c of faces x0 x1 y0 y1) (c of z0 z1, -, -)
+//                                   (lo.x, hi.x, lo.y, hi.y) (lo.z, hi.z, present mask, -) (c of faces x0 x1 y0 y1) (c of z0 z1, -, -)
+//                                   (pairs: one packed FADD2/FMUL2 handles both bounds / both faces of an axis)
 //   [cslot_off, ...)                int32 finite-plane slot per cluster face (6 per cluster, -1 = absent)
 //   [idx_off, ...)                  int32 object index per primitive: spheres, finite, infinite
 // Within each type the non-light primitives come first (counts *_nl): the shadow sweep
@@ -88,6 +89,7 @@ struct RenderLaunch {
     const int* row_order;    // optional: permutation of the rows [0, height) — of the 8-row tile rows [0, height/8) when
                              // `tiled` — in which the queue runs
     unsigned int* col_cost;  // optional (balancer pre-pass): [x1-x0] per column then [height] per row, += bounces of every finished pixel
+    int n_objects;           // objects of the scene (checked builds verify table indices against it)
     int refill_min;          // idle lanes a warp waits for before it takes new pixels (1..32)
     int tiled;               // queue positions map to 4x8-pixel tiles (band width % 4 == 0, height % 8 == 0)
 };
