@@ -23,6 +23,10 @@ METRICS = [
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "shared-memory bank conflicts"),
     ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "shared-memory wavefronts"),
     ("l1tex__t_sector_hit_rate.pct", "L1 hit rate %"),
+    ("smsp__sass_thread_inst_executed_op_fadd_pred_on.sum", "FADD thread instructions"),
+    ("smsp__sass_thread_inst_executed_op_fmul_pred_on.sum", "FMUL thread instructions"),
+    ("smsp__sass_thread_inst_executed_op_ffma_pred_on.sum", "FFMA thread instructions"),
+    ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "ALU-pipe instruction utilisation %"),
     ("dram__bytes_read.sum", "DRAM read"),
     ("dram__bytes_write.sum", "DRAM written"),
 ]
@@ -36,15 +40,29 @@ def raw(path):
     return {h: (vals[i], units[i]) for i, h in enumerate(hdr)}
 
 
+RAYS = {}
+
+
 def main():
     out_json = sys.argv[1]
-    caps = [a.split("=", 1) for a in sys.argv[2:]]
+    args = sys.argv[2:]
+    # rays:<label>=<n>  — rays of the captured launch (from the plain run of the same command)
+    for a in [a for a in args if a.startswith("rays:")]:
+        k, v = a[5:].split("=")
+        RAYS[k] = int(v)
+    caps = [a.split("=", 1) for a in args if not a.startswith("rays:")]
     data, table = {}, {}
     for label, path in caps:
         r = raw(path)
         table[label] = r
         rd, wr = r["dram__bytes_read.sum"], r["dram__bytes_write.sum"]
+        fp32 = sum(float(r[m][0]) for m in ("smsp__sass_thread_inst_executed_op_fadd_pred_on.sum",
+                                           "smsp__sass_thread_inst_executed_op_fmul_pred_on.sum",
+                                           "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum") if m in r)
+        rays = RAYS.get(label)
         data[label] = {
+            "fp32_lane_inst_per_launch": fp32 or None, "rays_per_launch": rays,
+            "fp32_lane_inst_per_ray": (fp32 / rays) if fp32 and rays else None,
             "capture": path.split("/")[-1],
             "kernel": r.get("Kernel Name", ("", ""))[0],
             "dram_bytes_per_launch": float(rd[0]) * UNIT[rd[1]] + float(wr[0]) * UNIT[wr[1]],

@@ -19,7 +19,7 @@ ctx.upload(scene, cam)
 p = api.default_params(w, h, d)
 for i in range(n):
     st = ctx.render_device(p)
-    print(name, "launch", i, "kernel ms", st.render_ms[0], "Mrays/s", st.rays / st.render_ms[0] / 1e3, flush=True)
+    print(name, "launch", i, "kernel ms", st.render_ms[0], "Mrays/s", st.rays / st.render_ms[0] / 1e3, "rays", st.rays, flush=True)
 if "--txt" in sys.argv:
     print("txt bytes", len(ctx.format_txt()))
 ctx.close()
