@@ -400,6 +400,15 @@ def test_image_outputs_and_camera_update(gpu_ctx, tmp_path):
     got = np.frombuffer(raw[len(head):], dtype=np.uint8).reshape(64, 96, 3)
     want = np.transpose(quant8(img), (1, 0, 2))[::-1].astype(np.uint8)
     assert np.array_equal(got, want)
+    # a frame that is not a multiple of the 32x32 transposition tile
+    p2 = api.default_params(97, 61, 4)
+    img2, _ = gpu_ctx.render(p2)
+    gpu_ctx.write_ppm(p2, str(tmp_path / "b.ppm"))
+    raw2 = (tmp_path / "b.ppm").read_bytes()
+    head2 = b"P6\n97 61\n255\n"
+    got2 = np.frombuffer(raw2[len(head2):], dtype=np.uint8).reshape(61, 97, 3)
+    assert np.array_equal(got2, np.transpose(quant8(img2), (1, 0, 2))[::-1].astype(np.uint8))
+    img, _ = gpu_ctx.render(p)
     gpu_ctx.write_bin(p, str(tmp_path / "a.bin"))
     rawb = (tmp_path / "a.bin").read_bytes()
     assert rawb[:8] == b"TCRTBIN1" and np.frombuffer(rawb[8:16], dtype=np.int32).tolist() == [96, 64]

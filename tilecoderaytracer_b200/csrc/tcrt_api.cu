@@ -1202,31 +1202,30 @@ int tcrt_write_ppm(tcrt_ctx* ctx, const tcrt_params* p, const char* path) {
     int rc = check_full_frame(ctx, p);
     if (rc) return rc;
     const size_t W = (size_t)p->width, H = (size_t)p->height;
-    std::vector<unsigned char> xmajor(W * H * 3);
-    // quantise each band on its device (the text scratch buffer doubles as the 8-bit staging area)
+    // every band is quantised AND turned into image rows on its device (the text scratch buffer doubles as the 8-bit
+    // staging area); a strided copy drops it into its columns of the host image: no per-pixel work on the host
+    std::vector<unsigned char> img(W * H * 3);
     for (auto& d : ctx->devs) {
         if (d.fr().x1 <= d.fr().x0) continue;
         CK(ctx, cudaSetDevice(d.dev));
-        const size_t nv = (size_t)(d.fr().x1 - d.fr().x0) * H * 3;
-        rc = ensure(ctx, d.text, d.text_cap, nv + 16);
-        if (rc) return rc;
+        const size_t cols = (size_t)(d.fr().x1 - d.fr().x0);
+        if (d.text_cap < cols * H * 3 + 16) {
+            if (d.text) CK(ctx, cudaFree(d.text));
+            d.text = nullptr;
+            d.text_cap = 0;
+            CK(ctx, cudaMalloc((void**)&d.text, cols * H * 3 + 16));
+            d.text_cap = cols * H * 3 + 16;
+        }
         ctx->txt_prepared = false;
-        CK(ctx, tcrt_launch_quantize8(d.fr().frame, nv, reinterpret_cast<unsigned char*>(d.text), d.stream));
-        CK(ctx, cudaMemcpyAsync(xmajor.data() + (size_t)d.fr().x0 * H * 3, d.text, nv, cudaMemcpyDeviceToHost, d.stream));
+        CK(ctx, tcrt_launch_quantize8_image(d.fr().frame, (int)cols, (int)H, reinterpret_cast<unsigned char*>(d.text), d.stream));
+        CK(ctx, cudaMemcpy2DAsync(img.data() + (size_t)d.fr().x0 * 3, W * 3, d.text, cols * 3, cols * 3, H,
+                                  cudaMemcpyDeviceToHost, d.stream));
     }
     for (auto& d : ctx->devs) {
         if (d.fr().x1 <= d.fr().x0) continue;
         CK(ctx, cudaSetDevice(d.dev));
         CK(ctx, cudaStreamSynchronize(d.stream));
     }
-    // x-major, z up  ->  image rows, top row first
-    std::vector<unsigned char> img(W * H * 3);
-    for (size_t x = 0; x < W; x++)
-        for (size_t z = 0; z < H; z++) {
-            const unsigned char* s = &xmajor[(x * H + z) * 3];
-            unsigned char* o = &img[((H - 1 - z) * W + x) * 3];
-            o[0] = s[0]; o[1] = s[1]; o[2] = s[2];
-        }
     char header[64];
     const int hn = snprintf(header, sizeof header, "P6\n%d %d\n255\n", p->width, p->height);
     int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0666);

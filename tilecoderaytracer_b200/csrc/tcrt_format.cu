@@ -304,21 +304,41 @@ cudaError_t tcrt_launch_fp32_peak(bool fma, float* scratch, int grid, int iters,
 
 // ---- 8-bit quantisation for the image outputs (tcrt_write_ppm) ------------------------------------------
 // q(c) = floor(clamp(c, 0, 1) * 255 + 0.5) on the float promoted to double: the quantisation the
-// parity tolerance is stated in (last row).  NaN -> 0.  Layout stays x-major; the host
-// turns it into image rows while writing (6 MB at 1080p).
+// parity tolerance is stated in (last row).  NaN -> 0.  The kernel also turns the x-major band
+// (column by column, z up) into image rows (top row first): a 32x32-pixel tile goes through shared memory, so
+// both the float reads (along z) and the byte writes (along x) are contiguous.
 namespace {
-__global__ void quantize8_kernel(const float* __restrict__ rgb, size_t n_values, unsigned char* __restrict__ out) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_values; i += (size_t)gridDim.x * blockDim.x) {
-        const double c = (double)rgb[i];
-        const double cl = c > 0.0 ? (c < 1.0 ? c : 1.0) : 0.0;   // NaN fails both compares -> 0
-        out[i] = (unsigned char)floor(cl * 255.0 + 0.5);
+__device__ __forceinline__ unsigned char quant8(float v) {
+    const double c = (double)v;
+    const double cl = c > 0.0 ? (c < 1.0 ? c : 1.0) : 0.0;   // NaN fails both compares -> 0
+    return (unsigned char)floor(cl * 255.0 + 0.5);
+}
+// rgb: cols x height pixels, x-major.  out: height rows of cols pixels, row 0 = z = height-1.
+__global__ void __launch_bounds__(256) quantize8_image_kernel(const float* __restrict__ rgb, int cols, int height,
+                                                              unsigned char* __restrict__ out) {
+    __shared__ unsigned char tile[32][32 * 3 + 1];     // [x in tile][z in tile][channel]
+    const int tiles_z = (height + 31) / 32, tiles_x = (cols + 31) / 32;
+    for (int t = blockIdx.x; t < tiles_x * tiles_z; t += gridDim.x) {
+        const int x0 = (t / tiles_z) * 32, z0 = (t % tiles_z) * 32;
+        for (int i = threadIdx.x; i < 32 * 96; i += 256) {       // 32 columns x (32 rows x 3 channels), contiguous along z
+            const int xx = i / 96, k = i % 96;
+            const int x = x0 + xx, z = z0 + k / 3;
+            if (x < cols && z < height) tile[xx][k] = quant8(rgb[((size_t)x * height + z0) * 3 + k]);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 32 * 96; i += 256) {       // 32 rows x (32 columns x 3 channels), contiguous along x
+            const int zz = i / 96, k = i % 96;
+            const int z = z0 + zz, x = x0 + k / 3;
+            if (x < cols && z < height) out[((size_t)(height - 1 - z) * cols + x0) * 3 + k] = tile[k / 3][zz * 3 + k % 3];
+        }
+        __syncthreads();
     }
 }
 }  // namespace
 
-cudaError_t tcrt_launch_quantize8(const float* rgb, size_t n_values, unsigned char* out, cudaStream_t stream) {
-    if (n_values == 0) return cudaSuccess;
-    const int grid = (int)min((n_values + 255) / 256, (size_t)148 * 16);
-    quantize8_kernel<<<grid, 256, 0, stream>>>(rgb, n_values, out);
+cudaError_t tcrt_launch_quantize8_image(const float* rgb, int cols, int height, unsigned char* out, cudaStream_t stream) {
+    if (cols <= 0 || height <= 0) return cudaSuccess;
+    const long long tiles = (long long)((cols + 31) / 32) * ((height + 31) / 32);
+    quantize8_image_kernel<<<(int)min(tiles, (long long)148 * 8), 256, 0, stream>>>(rgb, cols, height, out);
     return cudaGetLastError();
 }

@@ -4,7 +4,7 @@
 t="$1"; shift
 for i in $(seq 1 40); do
     out=$(/usr/local/graft/bin/gpurun ${GPUS:+--gpus $GPUS} --timeout "$t" -- "$@" 2>&1); rc=$?
-    if echo "$out" | grep -q "nothing was charged"; then sleep 45; continue; fi
+    if echo "$out" | grep -qE "nothing was charged|retry in [0-9]+s"; then sleep 60; continue; fi
     echo "$out" | tail -4
     exit $rc
 done
