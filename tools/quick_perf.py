@@ -31,7 +31,9 @@ if "--noparity" not in sys.argv:
         rays_ok = st.rays == cnt["rays_primary"] + cnt["rays_shadow"] + cnt["rays_reflect"]
         ok &= bad == 0 and rays_ok
         print(f"parity {name:16s} mismatch {bad:6d} rays_ok {rays_ok}", flush=True)
-cfgs = [("default", 1920, 1080, 5), ("default", 3840, 2160, 50), ("synth1024", 3840, 2160, 50)]
+cfgs = [("default", 500, 504, 50), ("default", 1920, 1080, 5), ("default", 3840, 2160, 50), ("synth1024", 3840, 2160, 50)]
+if "--bands" in sys.argv:      # one eighth of the 4K frame: what a GPU renders at N = 8 (latency of the deepest paths)
+    cfgs = [("default", 3840, 2160, 50)]
 if "--big" in sys.argv:
     cfgs += [("synth256", 7680, 4320, 10), ("two_mirrors", 1920, 1080, 50)]
 for name, w, h, d in cfgs:
@@ -41,7 +43,7 @@ for name, w, h, d in cfgs:
     p = api.default_params(w, h, d)
     ms = []
     for i in range(4):
-        st = ctx.render_device(p)
+        st = ctx.render_device(p, 0, w // 8) if "--bands" in sys.argv else ctx.render_device(p)
         ms.append(st.render_ms[0])
     best = min(ms[1:])
     print(f"perf {name:12s} {w}x{h} d{d}: {best:9.3f} ms  {st.rays / best / 1e3:9.1f} Mrays/s", flush=True)
