@@ -77,6 +77,9 @@ struct DeviceState {
     // balancer pre-pass: bounce counts per column, then per row (tcrt_balance_columns)
     unsigned int* col_cost = nullptr;
     size_t col_cost_cap = 0;
+    // wavefront scratch (tcrt_render_wave.cu)
+    void* wave_mem = nullptr;
+    size_t wave_bytes = 0;
     // L2 flush scratch
     void* flush = nullptr;
     size_t flush_bytes = 0;
@@ -182,6 +185,7 @@ void free_device(DeviceState& d) {
     cudaFree(d.flush);
     cudaFree(d.row_order);
     cudaFree(d.col_cost);
+    cudaFree(d.wave_mem);
     cudaFreeHost(d.h_txt);
     cudaFreeHost(d.txt_stage);
     for (auto& e : d.ev_txt)
@@ -978,7 +982,16 @@ static int launch_band(tcrt_ctx* ctx, DeviceState& d, const tcrt_params* p, int 
         }
         rl.row_order = d.row_order;
     }
-    CK(ctx, tcrt_launch_render(rl, d.sm_count, d.stream, launches));
+    // scratch of the wavefront path (large frames of sphere-BVH scenes): ray queues and per-path state of one chunk
+    const size_t wave_need = tcrt_wave_mem_needed(rl);
+    if (wave_need > d.wave_bytes) {
+        if (d.wave_mem) CK(ctx, cudaFree(d.wave_mem));
+        d.wave_mem = nullptr;
+        d.wave_bytes = 0;
+        CK(ctx, cudaMalloc(&d.wave_mem, wave_need));
+        d.wave_bytes = wave_need;
+    }
+    CK(ctx, tcrt_launch_render(rl, d.sm_count, d.stream, launches, d.wave_mem, d.wave_bytes));
     return TCRT_OK;
 }
 

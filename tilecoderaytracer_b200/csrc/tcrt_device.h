@@ -108,8 +108,16 @@ void tcrt_build_box_clusters(const float* fin_geom, const std::vector<int>& plan
                              std::vector<TcrtBoxCluster>& out);
 #endif
 
-// render kernels (tcrt_render.cu)
-cudaError_t tcrt_launch_render(const RenderLaunch& rl, int sm_count, cudaStream_t stream, int* launches);
+// render kernels (tcrt_render.cu).  wave_mem / wave_bytes: scratch for the wavefront path (tcrt_render_wave.cu), which
+// tcrt_launch_render takes for large frames of sphere-BVH scenes when the scratch is big enough (tcrt_wave_mem_needed).
+cudaError_t tcrt_launch_render(const RenderLaunch& rl, int sm_count, cudaStream_t stream, int* launches, void* wave_mem,
+                               size_t wave_bytes);
+// bytes of scratch the wavefront path wants for this launch, 0 when the launch does not take that path
+size_t tcrt_wave_mem_needed(const RenderLaunch& rl);
+bool tcrt_wave_applies(const RenderLaunch& rl, int fm);
+size_t tcrt_wave_mem_bytes(size_t band_pixels, int max_depth);
+cudaError_t tcrt_launch_render_wave(const RenderLaunch& rl, int fm, int sm_count, size_t smem_scene, void* mem, size_t mem_bytes,
+                                    cudaStream_t stream, int* launches);
 size_t tcrt_render_max_smem();
 // experimental task-pool kernel for sphere-BVH scenes (tcrt_render_pool.cu, developer builds only); smem_scene = bytes of the staged blob
 cudaError_t tcrt_launch_render_pool(const RenderLaunch& rl, int fm, int sm_count, size_t smem_scene, cudaStream_t stream);

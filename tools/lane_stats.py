@@ -13,6 +13,9 @@ from tilecoderaytracer_b200 import _ffi, api  # noqa: E402
 lib = _ffi.load()
 NAMES = {0: "bounce iterations", 2: "nearest: inner-node steps", 4: "nearest: leaf phases", 6: "shadow: inner-node steps",
          8: "shadow: leaf phases", 10: "shadow sweeps (per light)", 12: "light loops"}
+if "--wave" in sys.argv:
+    NAMES = {2: "trace: inner-node steps", 4: "trace: leaf phases", 6: "trace: fetch events (lanes taking a task)",
+             8: "trace: inner steps, lanes blocked on leaves", 12: "trace: inner steps, lanes without task"}
 if "--pool" in sys.argv:
     NAMES = {0: "iterations", 2: "pool: inner-node steps", 4: "pool: leaf phases", 6: "pool: fetch events (free lanes)",
              8: "pool: inner steps, lanes blocked on leaves", 12: "pool: inner steps, lanes without task",
@@ -26,7 +29,7 @@ for name in [a for a in sys.argv[1:] if not a.startswith("--")] or ["synth256_10
     p = api.default_params(w, h, d)
     ctx.render_device(p)
     out = (C.c_ulonglong * 16)()
-    fn = lib.tcrt_dev_lane_stats_pool if "--pool" in sys.argv else lib.tcrt_dev_lane_stats
+    fn = lib.tcrt_dev_lane_stats_pool if "--pool" in sys.argv else (lib.tcrt_dev_lane_stats_wave if "--wave" in sys.argv else lib.tcrt_dev_lane_stats)
     fn(out, 1)
     st = ctx.render_device(p)
     fn(out, 0)
