@@ -1623,6 +1623,38 @@ bool close_sink(TxtSink* s, size_t final_size) {
 
 extern "C" {
 
+// Streams every device's band through the pipe (one issuing thread per device, the caller's thread for device 0).
+// Exceptions of the C++ runtime (thread creation) must not cross the C boundary: they become TCRT_ERR_IO.
+static int stream_all_bands(tcrt_ctx* ctx, const TxtSink& sink, size_t base, bool* any_not_fixed, bool* io_error) {
+    const int nd = (int)ctx->devs.size();
+    std::vector<int> rcs(nd, TCRT_OK);
+    std::vector<unsigned int> not_fixed(nd, 0u);
+    std::vector<std::string> errs(nd);
+    TxtPipe pipe;
+    std::vector<std::thread> issuers;
+    try {
+        pipe.start(&sink, n_txt_workers());
+        for (int i = 1; i < nd; i++)
+            issuers.emplace_back([&, i] { rcs[i] = stream_band_fixed(ctx, ctx->devs[i], pipe, base, &not_fixed[i], &errs[i]); });
+        rcs[0] = stream_band_fixed(ctx, ctx->devs[0], pipe, base, &not_fixed[0], &errs[0]);
+        for (auto& t : issuers) t.join();
+        pipe.finish();
+    } catch (const std::exception& e) {
+        for (auto& t : issuers)
+            if (t.joinable()) t.join();
+        pipe.finish();
+        return fail(ctx, TCRT_ERR_IO, "writer threads: %s", e.what());
+    }
+    ctx->txt_prepared = false;
+    *any_not_fixed = false;
+    *io_error = pipe.io_error;
+    for (int i = 0; i < nd; i++) {
+        if (rcs[i]) return fail(ctx, rcs[i], "%s", errs[i].c_str());
+        *any_not_fixed = *any_not_fixed || not_fixed[i] != 0u;
+    }
+    return TCRT_OK;
+}
+
 // General layout (some line is not 31 bytes): per-pixel lengths -> scan -> byte stores, whole bands at a time.
 static int write_txt_general(tcrt_ctx* ctx, const char* path, const char* header, int hn) {
     size_t total = 0;
@@ -1659,28 +1691,13 @@ int tcrt_write_txt(tcrt_ctx* ctx, const tcrt_params* p, const char* path, double
     rc = open_sink(ctx, path, true, total, &sink);
     if (rc) return rc;
     sink.put(0, header, (size_t)hn);
-    TxtPipe pipe;
-    pipe.start(&sink, n_txt_workers());
-    const int nd = (int)ctx->devs.size();
-    std::vector<int> rcs(nd, TCRT_OK);
-    std::vector<unsigned int> not_fixed(nd, 0u);
-    std::vector<std::string> errs(nd);
-    std::vector<std::thread> issuers;
-    for (int i = 1; i < nd; i++)
-        issuers.emplace_back([&, i] { rcs[i] = stream_band_fixed(ctx, ctx->devs[i], pipe, (size_t)hn, &not_fixed[i], &errs[i]); });
-    rcs[0] = stream_band_fixed(ctx, ctx->devs[0], pipe, (size_t)hn, &not_fixed[0], &errs[0]);
-    for (auto& t : issuers) t.join();
-    pipe.finish();
-    ctx->txt_prepared = false;
-    bool general = false;
-    for (int i = 0; i < nd; i++) {
-        if (rcs[i]) {
-            close_sink(&sink, total);
-            return fail(ctx, rcs[i], "%s", errs[i].c_str());
-        }
-        general = general || not_fixed[i] != 0u;
+    bool general = false, io_error = false;
+    rc = stream_all_bands(ctx, sink, (size_t)hn, &general, &io_error);
+    if (rc) {
+        close_sink(&sink, total);
+        return rc;
     }
-    if (!close_sink(&sink, total) || pipe.io_error) return fail(ctx, TCRT_ERR_IO, "short write to %s", path);
+    if (!close_sink(&sink, total) || io_error) return fail(ctx, TCRT_ERR_IO, "short write to %s", path);
     if (general) return write_txt_general(ctx, path, header, hn);
     return TCRT_OK;
 }
@@ -1717,27 +1734,14 @@ int tcrt_write_txt_band(tcrt_ctx* ctx, const tcrt_params* p, const char* path, d
     }
     sink.size = total;
     map_sink(&sink);
-    TxtPipe pipe;
-    pipe.start(&sink, n_txt_workers());
-    const int nd = (int)ctx->devs.size();
-    std::vector<int> rcs(nd, TCRT_OK);
-    std::vector<unsigned int> not_fixed(nd, 0u);
-    std::vector<std::string> errs(nd);
-    std::vector<std::thread> issuers;
-    for (int i = 1; i < nd; i++)
-        issuers.emplace_back([&, i] { rcs[i] = stream_band_fixed(ctx, ctx->devs[i], pipe, (size_t)hn, &not_fixed[i], &errs[i]); });
-    rcs[0] = stream_band_fixed(ctx, ctx->devs[0], pipe, (size_t)hn, &not_fixed[0], &errs[0]);
-    for (auto& t : issuers) t.join();
-    pipe.finish();
-    ctx->txt_prepared = false;
+    bool not_fixed = false, io_error = false;
+    rc = stream_all_bands(ctx, sink, (size_t)hn, &not_fixed, &io_error);
     const bool closed = close_sink(&sink, total);
-    for (int i = 0; i < nd; i++) {
-        if (rcs[i]) return fail(ctx, rcs[i], "%s", errs[i].c_str());
-        if (not_fixed[i])
-            return fail(ctx, TCRT_ERR_UNSUPPORTED, "a pixel line of this band is not 31 bytes (a channel >= 10, negative or not finite): "
-                                                   "gather the bands and use tcrt_write_txt");
-    }
-    if (!closed || pipe.io_error) return fail(ctx, TCRT_ERR_IO, "short write to %s", path);
+    if (rc) return rc;
+    if (not_fixed)
+        return fail(ctx, TCRT_ERR_UNSUPPORTED, "a pixel line of this band is not 31 bytes (a channel >= 10, negative or not finite): "
+                                               "gather the bands and use tcrt_write_txt");
+    if (!closed || io_error) return fail(ctx, TCRT_ERR_IO, "short write to %s", path);
     return TCRT_OK;
 }
 
