@@ -122,8 +122,8 @@ struct tcrt_ctx {
     size_t scene_total_f4 = 0;
     int n_objects = 0;
     DeviceScene scene_ds{};
-    size_t scene_off[7] = {};       // surface, material, normals, frame, tex, bvh_s, bvh_f
-    bool scene_bvh_s = false, scene_bvh_f = false;
+    size_t scene_off[9] = {};       // surface, material, normals, frame, tex, bvh_s, bvh_f, grid cells, grid items
+    bool scene_bvh_s = false, scene_bvh_f = false, scene_grid = false;
 };
 
 namespace {
@@ -440,6 +440,8 @@ static int build_scene_blob(tcrt_ctx* ctx, const tcrt_scene* s) {
     // type's array is re-ordered into leaf order.  `n_*_nl` keeps meaning "non-light" (the shadow
     // sweep's range); `n_*_bvh` <= n_*_nl is the BVH-covered prefix, the rest is swept linearly.
     std::vector<float4> bvh_s, bvh_f;
+    TcrtSphereGrid grid;
+    bool has_grid = false;
     int bvh_depth_s = 0, bvh_depth_f = 0;
     std::vector<TcrtBoxCluster> clusters;
     ds.n_fin_gen = ds.n_fin_nl;
@@ -493,6 +495,12 @@ static int build_scene_blob(tcrt_ctx* ctx, const tcrt_scene* s) {
             ps.swap(np);
             ds.n_sph_bvh = nb;
             ds.bvh_rmin = rmin * 0.999f;
+            // a uniform grid over the same spheres (leaf order), when they are even enough for one (tcrt_bvh.cpp)
+            if (!bvh_s.empty()) {
+                std::vector<float> leaf_boxes(6 * (size_t)nb);
+                for (int k = 0; k < nb; k++) memcpy(&leaf_boxes[6 * (size_t)k], &boxes_s[6 * (size_t)ord[k]], 6 * sizeof(float));
+                has_grid = tcrt_build_sphere_grid(leaf_boxes, nb, grid);
+            }
             // The tree collapsed into one leaf (few spheres left after the exclusions, or SAH keeps
             // <= 8 coincident ones together): there are no nodes, the kernel variant without a sphere
             // BVH runs, and it stages and sweeps EVERY sphere — so none may count as BVH-covered.
@@ -590,7 +598,11 @@ static int build_scene_blob(tcrt_ctx* ctx, const tcrt_scene* s) {
     const size_t off_tex = off_frame + 3 * (size_t)ds.n_inf;
     const size_t off_bvh_s = off_tex + 2 * (size_t)s->n_textures;
     const size_t off_bvh_f = off_bvh_s + bvh_s.size();
-    const size_t total_f4 = off_bvh_f + bvh_f.size() + 1;
+    // the grid serves the kernels without finite-plane structures (FM 0 / 3); elsewhere the sphere BVH alone
+    has_grid = has_grid && !bvh_s.empty() && bvh_f.empty() && clusters.empty();
+    const size_t off_grid_cells = off_bvh_f + bvh_f.size();
+    const size_t off_grid_items = off_grid_cells + (has_grid ? (grid.cell_start.size() + 3) / 4 : 0);
+    const size_t total_f4 = off_grid_items + (has_grid ? (grid.items.size() + 3) / 4 : 0) + 1;
     std::vector<float4> host(total_f4, make_float4(0.f, 0.f, 0.f, 0.f));
     auto f4 = [](const float* p) { return make_float4(p[0], p[1], p[2], p[3]); };
     int* idx = reinterpret_cast<int*>(&host[ds.idx_off]);
@@ -677,6 +689,17 @@ static int build_scene_blob(tcrt_ctx* ctx, const tcrt_scene* s) {
     }
     std::copy(bvh_s.begin(), bvh_s.end(), host.begin() + off_bvh_s);
     std::copy(bvh_f.begin(), bvh_f.end(), host.begin() + off_bvh_f);
+    if (has_grid) {
+        memcpy(&host[off_grid_cells], grid.cell_start.data(), grid.cell_start.size() * sizeof(int));
+        memcpy(&host[off_grid_items], grid.items.data(), grid.items.size() * sizeof(int));
+        for (int k = 0; k < 3; k++) {
+            ds.grid_lo[k] = grid.lo[k];
+            ds.grid_cell[k] = grid.cell[k];
+            ds.grid_inv_cell[k] = 1.0f / grid.cell[k];
+            ds.grid_dims[k] = grid.dims[k];
+        }
+        ds.grid_margin = grid.reg_margin;
+    }
 
     // into the pinned staging buffer (once every device has finished reading the previous scene out of it)
     for (auto& d : ctx->devs) {
@@ -701,6 +724,9 @@ static int build_scene_blob(tcrt_ctx* ctx, const tcrt_scene* s) {
     ctx->scene_off[4] = off_tex;
     ctx->scene_off[5] = off_bvh_s;
     ctx->scene_off[6] = off_bvh_f;
+    ctx->scene_off[7] = off_grid_cells;
+    ctx->scene_off[8] = off_grid_items;
+    ctx->scene_grid = has_grid;
     ctx->scene_bvh_s = !bvh_s.empty();
     ctx->scene_bvh_f = !bvh_f.empty();
     return TCRT_OK;
@@ -726,6 +752,8 @@ static int send_scene(tcrt_ctx* ctx, const tcrt_camera* cam) {
         d.ds.obj_info = nullptr;
         d.ds.bvh_sph = ctx->scene_bvh_s ? d.scene_mem + ctx->scene_off[5] : nullptr;
         d.ds.bvh_fin = ctx->scene_bvh_f ? d.scene_mem + ctx->scene_off[6] : nullptr;
+        d.ds.grid_cells = ctx->scene_grid ? reinterpret_cast<const int*>(d.scene_mem + ctx->scene_off[7]) : nullptr;
+        d.ds.grid_items = ctx->scene_grid ? reinterpret_cast<const int*>(d.scene_mem + ctx->scene_off[8]) : nullptr;
     }
     ctx->cam = *cam;
     ctx->cut_valid = false;

@@ -132,3 +132,138 @@ int tcrt_build_bvh(const std::vector<float>& boxes, int n, std::vector<int>& ord
     if (depth) *depth = b.max_depth;
     return root;
 }
+
+// ---- uniform grid over the BVH-covered spheres -------------------------------------------------------------------------------
+// Scenes of many similar spheres (BASELINE configs 3 and 4: lattices of 1024 / 256 spheres) are walked faster with a 3D-DDA
+// through a uniform grid than through a binary tree: a step costs a third of a tree node, and a ray meets a sphere after a few
+// cells.  Like the BVH the grid only PRUNES: a sphere is registered in every cell its box — inflated by `reg_margin`, which
+// must cover the per-ray fattening of the kernel (tcrt_render_common.cuh `fatten`) — overlaps, and spheres found in a cell are
+// tested with the reference's exact arithmetic.  Rays whose fattening exceeds the margin (origins far from the scene) use the
+// BVH, which therefore always exists next to the grid.
+//   boxes: n x 6 floats (lo xyz, hi xyz) of the spheres in leaf order, already inflated like the BVH's.
+// Returns false (no grid) when the spheres are too uneven for a grid to pay: more than 8 registrations per sphere on average,
+// or a cell with more than 24 spheres.
+bool tcrt_build_sphere_grid(const std::vector<float>& boxes, int n, TcrtSphereGrid& g) {
+    g = TcrtSphereGrid{};
+    if (n < 24) return false;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    std::vector<double> ext;
+    ext.reserve(n);
+    for (int i = 0; i < n; i++) {
+        double e = 0;
+        for (int k = 0; k < 3; k++) {
+            const double a = boxes[6 * i + k], b = boxes[6 * i + 3 + k];
+            if (!std::isfinite(a) || !std::isfinite(b) || !(b >= a)) return false;
+            lo[k] = std::min(lo[k], a);
+            hi[k] = std::max(hi[k], b);
+            e = std::max(e, b - a);
+        }
+        ext.push_back(e);
+    }
+    std::sort(ext.begin(), ext.end());
+    const double d_med = ext[n / 2], d_max = ext[n - 1];
+    if (!(d_med > 0) || d_max > 4.0 * d_med) return false;            // one huge sphere would sit in every cell
+    double vol = 1.0;
+    for (int k = 0; k < 3; k++) vol *= std::max(hi[k] - lo[k], d_med);
+    // Cell size and phase per axis.  Cost of a ray per unit of length: (cells entered) x (a DDA step + the spheres tested in
+    // a cell) ~ (sum_k 1/c_k) x (S + T * n/V * prod_k(ov_k * c_k)), ov_k = cells a sphere overlaps along axis k.  A grid in
+    // step with a lattice of spheres (cell = spacing, every sphere inside one cell) tests each sphere once; out of step it
+    // registers a sphere in two cells per axis and tests eight times as many.  Coordinate descent over the axes: each takes the
+    // (size, phase) minimising the model, sizes from 0.7 to 3 typical diameters, 32 phases, starting at one sphere per cell.
+    const double guess = std::max(1.15 * d_med, cbrt(vol / n));
+    const double margin = 0.02 * std::min(guess, 1.15 * d_med);
+    const double kStep = 25.0, kTest = 30.0;        // instructions: one DDA step, one sphere test
+    double cs[3] = {guess, guess, guess}, org[3], ovm[3] = {2.0, 2.0, 2.0};
+    for (int k = 0; k < 3; k++) org[k] = lo[k] - 2.0 * margin;
+    auto mean_overlap = [&](int k, double c, double o) {
+        double ov = 0.0;
+        for (int i = 0; i < n; i++)
+            ov += floor(((double)boxes[6 * i + 3 + k] + margin - o) / c) - floor(((double)boxes[6 * i + k] - margin - o) / c) + 1.0;
+        return ov / n;
+    };
+    auto model = [&](const double* c, const double* ov) {
+        return (1.0 / c[0] + 1.0 / c[1] + 1.0 / c[2]) * (kStep + kTest * n / vol * (ov[0] * c[0]) * (ov[1] * c[1]) * (ov[2] * c[2]));
+    };
+    for (int k = 0; k < 3; k++) ovm[k] = mean_overlap(k, cs[k], org[k]);
+    for (int round = 0; round < 3; round++) {
+        for (int k = 0; k < 3; k++) {
+            double best = model(cs, ovm), c_try[3] = {cs[0], cs[1], cs[2]}, ov_try[3] = {ovm[0], ovm[1], ovm[2]};
+            // coarse: 40 sizes on a geometric scale; fine: +-4 % around the current size in 0.25 % steps (a lattice's own
+            // spacing has to be met within a fraction of the gap between its spheres)
+            const double c_now = cs[k];
+            for (int ci = 0; ci < 40 + 33; ci++) {
+                const double c = ci < 40 ? 0.7 * d_med * pow(3.0 / 0.7, ci / 39.0) : c_now * (1.0 + 0.0025 * (ci - 40 - 16));
+                if ((hi[k] - lo[k] + 4.0 * margin) / c > 63.0) continue;                 // at most 64 cells per axis
+                for (int ph = 0; ph < 32; ph++) {
+                    const double o = lo[k] - 2.0 * margin - c * ph / 32.0;
+                    c_try[k] = c;
+                    ov_try[k] = mean_overlap(k, c, o);
+                    const double f = model(c_try, ov_try);
+                    if (f < best * (1.0 - 1e-9)) {
+                        best = f;
+                        cs[k] = c;
+                        org[k] = o;
+                        ovm[k] = ov_try[k];
+                    }
+                }
+            }
+        }
+    }
+    int dims[3];
+    for (int k = 0; k < 3; k++) {
+        lo[k] = org[k];
+        hi[k] += 2.0 * margin;
+        dims[k] = (int)std::min(64.0, std::max(1.0, ceil((hi[k] - lo[k]) / cs[k])));
+        if (lo[k] + cs[k] * dims[k] < hi[k]) cs[k] = (hi[k] - lo[k]) / dims[k];      // clamped: wider cells cover the rest
+    }
+    const size_t n_cells = (size_t)dims[0] * dims[1] * dims[2];
+    std::vector<int> count(n_cells + 1, 0);
+    auto range = [&](int i, int k, int& a, int& b) {
+        a = (int)floor(((double)boxes[6 * i + k] - margin - lo[k]) / cs[k]);
+        b = (int)floor(((double)boxes[6 * i + 3 + k] + margin - lo[k]) / cs[k]);
+        a = std::max(0, std::min(dims[k] - 1, a));
+        b = std::max(0, std::min(dims[k] - 1, b));
+    };
+    size_t total = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        if (pass == 1) {
+            if (total > (size_t)8 * n) return false;
+            for (size_t c = 0; c < n_cells; c++) {
+                if (count[c] > 24) return false;
+            }
+            // exclusive prefix sums -> cell starts
+            int run = 0;
+            for (size_t c = 0; c <= n_cells; c++) {
+                const int v = c < n_cells ? count[c] : 0;
+                count[c] = run;
+                run += v;
+            }
+            g.items.assign(total, 0);
+        }
+        std::vector<int> fill;
+        if (pass == 1) fill.assign(count.begin(), count.end() - 1);
+        for (int i = 0; i < n; i++) {
+            int a[3], b[3];
+            for (int k = 0; k < 3; k++) range(i, k, a[k], b[k]);
+            for (int z = a[2]; z <= b[2]; z++)
+                for (int y = a[1]; y <= b[1]; y++)
+                    for (int x = a[0]; x <= b[0]; x++) {
+                        const size_t c = (size_t)x + (size_t)dims[0] * ((size_t)y + (size_t)dims[1] * z);
+                        if (pass == 0) {
+                            count[c]++;
+                            total++;
+                        } else {
+                            g.items[fill[c]++] = i;
+                        }
+                    }
+        }
+    }
+    g.cell_start = count;
+    for (int k = 0; k < 3; k++) {
+        g.lo[k] = (float)lo[k];
+        g.cell[k] = (float)cs[k];
+        g.dims[k] = dims[k];
+    }
+    g.reg_margin = (float)(0.5 * margin);     // what a ray's fattening may be: half of what the registration allowed for
+    return true;
+}

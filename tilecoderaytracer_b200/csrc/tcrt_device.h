@@ -53,6 +53,13 @@ struct DeviceScene {
     const float4* bvh_sph;
     const float4* bvh_fin;
     int bvh_sph_root, bvh_fin_root;   // encoded like a child reference
+    // optional uniform grid over the BVH-covered spheres (nullptr = none): a 3D-DDA finds the cells a ray crosses,
+    // the spheres registered in a cell are tested exactly.  Rays fattened by more than grid_margin use the BVH.
+    const int* grid_cells;            // cell -> first item; n_cells + 1 entries
+    const int* grid_items;            // sphere slots
+    float grid_lo[3], grid_cell[3], grid_inv_cell[3];
+    int grid_dims[3];
+    float grid_margin;
     // per-ray fattening of the boxes (tcrt_render.cu `fatten`): bounding sphere (centre, radius^2)
     // of everything inside the BVHs, smallest BVH sphere radius, largest |coordinate|
     float bvh_cx, bvh_cy, bvh_cz, bvh_r2, bvh_rmin, bvh_cmax;
@@ -66,6 +73,16 @@ struct DeviceScene {
 int tcrt_build_bvh(const std::vector<float>& boxes, int n, std::vector<int>& order, std::vector<float4>& nodes,
                    int* depth);   // *depth: deepest node; the kernel's traversal stack holds TCRT_BVH_STACK entries
 #define TCRT_BVH_STACK 48
+// host builder of the uniform grid over the BVH-covered spheres (tcrt_bvh.cpp)
+struct TcrtSphereGrid {
+    float lo[3] = {0, 0, 0};
+    float cell[3] = {1, 1, 1};
+    int dims[3] = {0, 0, 0};
+    float reg_margin = 0.f;             // a ray whose fattening is below this may use the grid
+    std::vector<int> cell_start;        // dims[0]*dims[1]*dims[2] + 1
+    std::vector<int> items;             // sphere slots (leaf order), cell by cell
+};
+bool tcrt_build_sphere_grid(const std::vector<float>& boxes, int n, TcrtSphereGrid& g);
 #endif
 
 // Pixel tile of one queue claim: TCRT_TILE_W columns x TCRT_TILE_H rows = 32 pixels, one per lane.
@@ -119,6 +136,8 @@ size_t tcrt_wave_mem_bytes(size_t band_pixels, int max_depth);
 cudaError_t tcrt_launch_render_wave(const RenderLaunch& rl, int fm, int sm_count, size_t smem_scene, void* mem, size_t mem_bytes,
                                     cudaStream_t stream, int* launches);
 size_t tcrt_render_max_smem();
+// kernel for scenes whose spheres sit in a uniform grid (tcrt_render_grid.cu); smem = bytes of the staged blob
+cudaError_t tcrt_launch_render_grid(const RenderLaunch& rl, int fm, int sm_count, size_t smem, cudaStream_t stream);
 // experimental task-pool kernel for sphere-BVH scenes (tcrt_render_pool.cu, developer builds only); smem_scene = bytes of the staged blob
 cudaError_t tcrt_launch_render_pool(const RenderLaunch& rl, int fm, int sm_count, size_t smem_scene, cudaStream_t stream);
 // n random (a.xyz, b) cases: div3 (shared-reciprocal division of the render kernel) vs __fdiv_rn; *bad += mismatches
