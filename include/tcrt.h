@@ -163,6 +163,12 @@ void tcrt_free_host(void* p);
  * visible to calculatePixel through the global my_scene / my_camera (RayTracer.h:50-51). */
 int tcrt_upload_scene(tcrt_ctx* ctx, const tcrt_scene* scene, const tcrt_camera* camera);
 
+/* Which pruning structures the uploaded scene got (none of them can change a result; tests assert that the intended
+ * kernel path is exercised): info[0] spheres in the sphere BVH, [1] cells of the uniform sphere grid (0: none), [2] finite
+ * planes in their BVH, [3] box clusters, [4] rectangles owned by clusters, [5] spheres swept linearly, [6] finite planes
+ * swept linearly, [7] bytes of scene staged into shared memory per CTA. */
+int tcrt_scene_structures(tcrt_ctx* ctx, int info[8]);
+
 /* ---- render (replaces the pixel loop RayTracer.cpp:911-923) ----------------------- */
 /* Whole image -> host_rgb[width*height*3], x-major, z fastest, (r,g,b) float32: the layout
  * of the reference's pixels[W][H] (RayTracer.h:44).  stats may be NULL. */

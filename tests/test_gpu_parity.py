@@ -74,7 +74,7 @@ def test_axis_aligned_box_scenes_bit_exact(gpu_ctx, seed, n):
     check_counters(stats, cnt)
 
 
-@pytest.mark.parametrize("scene_name", ["default", "boxes:3:14", "boxes:7:9", "two_mirrors"])
+@pytest.mark.parametrize("scene_name", ["default", "boxes:3:14", "boxes:7:9", "two_mirrors", "synth256", "synth1024"])
 def test_axis_parallel_rays(gpu_ctx, scene_name):
     """A camera looking straight down +y with an axis-aligned screen: the centre column has D.x == 0
     and the centre row D.z == 0 exactly, and every mirror bounce off an axis-aligned face keeps such
@@ -497,6 +497,23 @@ def _lights_and_ground(s):
         .setReflectiveFactor(.5).setDiffuseFactor(.5)
 
 
+def test_named_scenes_take_their_intended_structures(gpu_ctx):
+    """default: box clusters, no BVH; synth256 / synth1024: sphere grid (+ BVH for far origins); SCENE 2: sphere BVH only (its
+    radius-10 sphere rules a grid out); a random scene with many finite planes: their BVH."""
+    want = {"default": dict(grid_cells=0, bvh_spheres=0, clusters=4, cluster_rects=24), "synth256": dict(bvh_spheres=256), "synth1024": dict(bvh_spheres=1024),
+            "two_mirrors": dict(grid_cells=0), "random:27:1500": dict(grid_cells=0)}
+    for name, exp in want.items():
+        scene, cam = make_scene(name)
+        gpu_ctx.upload(scene, cam)
+        got = gpu_ctx.scene_structures()
+        for k, v in exp.items():
+            assert got[k] == v, (name, got)
+        if name.startswith("synth"):
+            assert got["grid_cells"] > 0, (name, got)
+        if name in ("two_mirrors", "random:27:1500"):
+            assert got["bvh_spheres"] > 0 or got["bvh_finite"] > 0, (name, got)
+
+
 def test_sphere_bvh_collapsing_into_one_leaf(gpu_ctx):
     """>= 24 non-light spheres ask for a BVH, but after the exclusions (16 tiny spheres stay linear) only
     8 coincident ones are left and SAH keeps them in ONE leaf: there are no nodes, the kernel without a
@@ -653,3 +670,61 @@ def test_scene_cache_sees_every_change(gpu_ctx):
         want, cnt = O.render(s.flatten(), cam.export(), p)
         assert_bit_identical(img, want, f"shift {shift} color {color}")
         check_counters(stats, cnt)
+
+
+# ---- round 2: the uniform grid over lattice-like sphere scenes (tcrt_render_grid.cu) ---------------------------------------
+
+def _lattice(s, nx, ny, nz, spacing, radius, jitter=0.0, rvar=0.0, seed=1):
+    rng = np.random.default_rng(seed)
+    for k in range(nz):
+        for j in range(ny):
+            for i in range(nx):
+                c = np.array([-3 + spacing * i, -1 + spacing * j, radius + .05 + spacing * k]) + jitter * (rng.random(3) - .5)
+                r = radius * (1 + rvar * (rng.random() - .5))
+                s.addSphere(tuple(float(x) for x in c), float(r)).setColor(*(float(x) for x in rng.random(3))) \
+                    .setReflectiveFactor(float(.9 if (i + j + k) % 2 else 0.0)).setDiffuseFactor(.3)
+
+
+@pytest.mark.parametrize("case", ["far_camera", "inside_sphere", "jittered", "row_of_200", "dense_small", "three_lights"])
+def test_sphere_grid_edge_cases(gpu_ctx, case):
+    """Scenes whose spheres go into the uniform grid, rendered bit for bit like the oracle: a camera 600 units away
+    (every primary ray's fattening exceeds the grid's margin: BVH fallback, and far ground hits send far shadow and
+    mirror rays), a camera inside a sphere of the lattice (negative distances win), jittered positions and radii
+    (spheres registered in several cells), a row of 200 spheres (more cells than the 64 per axis the grid allows),
+    a dense lattice of small spheres, and three lights (three shadow passes per bounce)."""
+    cam = api.Camera()
+    c = cam.export()
+    s = api.Scene()
+    _lights_and_ground(s)
+    w, h, d = 128, 96, 8
+    if case == "far_camera":
+        _lattice(s, 6, 6, 3, 1.8, .75)
+        for k in range(3):      # move eye and screen 600 units back along the viewing direction (0.62, 0.78, 0.08)
+            shift = 600.0 * (.62, .78, .08)[k]
+            c.eye[k] -= shift
+            c.screen_origin[k] -= shift
+        w, h = 96, 64
+    elif case == "inside_sphere":
+        _lattice(s, 5, 5, 3, 1.8, .75)
+        eye = (-3 + 1.8 * 2 + .1, -1 + 1.8 * 2 - .2, .8 + 1.8)       # inside the sphere (2, 2, 1)
+        for k in range(3):
+            delta = eye[k] - c.eye[k]
+            c.eye[k] += delta
+            c.screen_origin[k] += delta
+    elif case == "jittered":
+        _lattice(s, 7, 7, 3, 1.5, .5, jitter=.5, rvar=.8, seed=7)
+    elif case == "row_of_200":
+        for i in range(200):
+            s.addSphere((-40 + 1.0 * i, 6 + .01 * i, .45), .4).setColor(i % 2, .5, 1 - i % 2).setReflectiveFactor(.7 if i % 3 == 0 else 0.0)
+    elif case == "dense_small":
+        _lattice(s, 12, 12, 3, .5, .2, jitter=.05, rvar=.2, seed=3)
+    else:
+        s.addSphere((3, -5, 9), .2).setAsLightSource(.6)
+        _lattice(s, 6, 6, 2, 1.8, .75)
+    p = api.default_params(w, h, d)
+    gpu_ctx.upload_flat(s.flatten(), c)
+    assert gpu_ctx.scene_structures()["grid_cells"] > 0, gpu_ctx.scene_structures()      # the scene does take the grid kernel
+    img, stats = gpu_ctx.render(p)
+    want, cnt = O.render(s.flatten(), c, p)
+    assert_bit_identical(img, want, f"sphere grid: {case}")
+    check_counters(stats, cnt)

@@ -248,6 +248,13 @@ class Context:
     def upload_flat(self, flat: TcrtScene, cam: TcrtCamera) -> None:
         self._ck(self._lib.tcrt_upload_scene(self._h, C.byref(flat), C.byref(cam)))
 
+    def scene_structures(self) -> dict:
+        """Which pruning structures the uploaded scene got (tcrt_scene_structures)."""
+        info = (C.c_int * 8)()
+        self._ck(self._lib.tcrt_scene_structures(self._h, info))
+        keys = ("bvh_spheres", "grid_cells", "bvh_finite", "clusters", "cluster_rects", "linear_spheres", "linear_finite", "staged_bytes")
+        return dict(zip(keys, (int(v) for v in info)))
+
     def render(self, params: TcrtParams, x0: int = 0, x1: Optional[int] = None, out: Optional[np.ndarray] = None):
         """Render columns [x0,x1) to host memory; returns (array[x1-x0, H, 3] float32, RenderStats)."""
         x1 = params.width if x1 is None else x1

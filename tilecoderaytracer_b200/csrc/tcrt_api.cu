@@ -1209,6 +1209,21 @@ int tcrt_fp32_peak(tcrt_ctx* ctx, double* unfused, double* fma, double* ms_each)
     return TCRT_OK;
 }
 
+int tcrt_scene_structures(tcrt_ctx* ctx, int info[8]) {
+    if (!ctx || !info) return fail(ctx, TCRT_ERR_INVALID, "null argument");
+    if (!ctx->has_scene) return fail(ctx, TCRT_ERR_NO_SCENE, "tcrt_upload_scene has not been called");
+    const DeviceScene& ds = ctx->scene_ds;
+    info[0] = ctx->scene_bvh_s ? ds.n_sph_bvh : 0;                                          // spheres in the sphere BVH
+    info[1] = ctx->scene_grid ? ds.grid_dims[0] * ds.grid_dims[1] * ds.grid_dims[2] : 0;     // cells of the sphere grid
+    info[2] = ctx->scene_bvh_f ? ds.n_fin_bvh : 0;                                          // finite planes in their BVH
+    info[3] = ds.n_clu;                                                                     // box clusters
+    info[4] = ds.n_arect;                                                                   // rectangles owned by clusters
+    info[5] = ds.n_sph - (ctx->scene_bvh_s ? ds.n_sph_bvh : 0);                             // spheres swept linearly
+    info[6] = ds.n_fin - ds.n_arect - (ctx->scene_bvh_f ? ds.n_fin_bvh : 0);                // finite planes swept linearly
+    info[7] = (int)((size_t)(ds.blob_f4 - ds.stage_off) * sizeof(float4));                  // bytes staged per CTA
+    return TCRT_OK;
+}
+
 int tcrt_set_camera(tcrt_ctx* ctx, const tcrt_camera* cam) {
     if (!ctx || !cam) return fail(ctx, TCRT_ERR_INVALID, "null argument");
     if (!ctx->has_scene) return fail(ctx, TCRT_ERR_NO_SCENE, "tcrt_upload_scene has not been called");
