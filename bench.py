@@ -201,7 +201,7 @@ def run_reference(args):
         return 0
     scene, w, h, depth = WORKLOADS[args.workload]
     if not have_reference():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_render not built"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/ref_render not built"})
         return 0
     cores = os.cpu_count() or 1
     procs = min(cores, w)
@@ -232,7 +232,7 @@ def run_reference(args):
         "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -758,7 +758,7 @@ def run_ours(args):
         if world == 1 and not inproc and not args.no_cpu_baseline and not args.quick:
             line["cpu_baseline"] = cpu_baseline(scene_name, w, h, depth)
         line["bench_wall_s"] = time.perf_counter() - t_start
-        print(json.dumps(line))
+        emit(line)
     ctx.close()
     dist.D.shutdown()
     return 0
@@ -778,6 +778,28 @@ def wait_for_build(paths, timeout_s=600.0):
     raise SystemExit("timed out waiting for local rank 0 to build " + ", ".join(paths))
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """The one JSON line of the contract, on the process's original stdout."""
+    text = json.dumps(line) + "\n"
+    if _RESULT_FD is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, text.encode())
+
+
+def quiet_stdout():
+    """Point fd 1 at stderr for the rest of the run (NCCL prints its version banner to stdout from C, build steps
+    chat): stdout then carries the JSON line and nothing else."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -788,6 +810,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="headline workload only (developer loop)")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         # the prebuilt oracle/_ref travels with the repo; built here only where /root/reference exists
         if int(os.environ.get("RANK", "0")) == 0 and not have_reference() and os.path.isdir("/root/reference"):
