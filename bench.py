@@ -146,7 +146,7 @@ def workload_config(name, n_gpus):
     how = "" if world > 1 or n_gpus == 1 else " (one process, multi-device tcrt_ctx)"
     return {"workload": name, "scene": scene, "width": w, "height": h, "max_depth": depth, "shadows": True,
             "reflections": True, "partition": f"{n_gpus} cost-balanced column band(s), one per GPU, no collective" + how,
-            "l2": "flushed between timed steps (the kernel reads no large input: scene lives in shared memory)"}
+            "l2": "flushed between timed steps (the kernel reads no large input: the scene is a few KB in shared memory, BVH nodes and grid cells a few hundred KB read through L1)"}
 
 
 # ---- the reference on the host cores (no import of the product anywhere below) -------------------------------
