@@ -601,7 +601,8 @@ static int build_scene_blob(tcrt_ctx* ctx, const tcrt_scene* s) {
     // the grid serves the kernels without finite-plane structures (FM 0 / 3); elsewhere the sphere BVH alone
     has_grid = has_grid && !bvh_s.empty() && bvh_f.empty() && clusters.empty();
     const size_t off_grid_cells = off_bvh_f + bvh_f.size();
-    const size_t off_grid_items = off_grid_cells + (has_grid ? (grid.cell_start.size() + 3) / 4 : 0);
+    const size_t n_grid_cells = has_grid ? grid.cell_start.size() - 1 : 0;
+    const size_t off_grid_items = off_grid_cells + 2 * n_grid_cells;
     const size_t total_f4 = off_grid_items + (has_grid ? (grid.items.size() + 3) / 4 : 0) + 1;
     std::vector<float4> host(total_f4, make_float4(0.f, 0.f, 0.f, 0.f));
     auto f4 = [](const float* p) { return make_float4(p[0], p[1], p[2], p[3]); };
@@ -690,7 +691,13 @@ static int build_scene_blob(tcrt_ctx* ctx, const tcrt_scene* s) {
     std::copy(bvh_s.begin(), bvh_s.end(), host.begin() + off_bvh_s);
     std::copy(bvh_f.begin(), bvh_f.end(), host.begin() + off_bvh_f);
     if (has_grid) {
-        memcpy(&host[off_grid_cells], grid.cell_start.data(), grid.cell_start.size() * sizeof(int));
+        // cell record: the first sphere's geometry next to the cell's count, so a one-sphere cell is one round of loads
+        for (size_t c = 0; c < n_grid_cells; c++) {
+            const int j0 = grid.cell_start[c], cnt = grid.cell_start[c + 1] - j0;
+            int4 meta = make_int4(cnt, cnt > 0 ? grid.items[j0] : 0, j0 + 1, 0);
+            if (cnt > 0) host[off_grid_cells + 2 * c] = host[grid.items[j0]];     // spheres sit at the front of the blob
+            memcpy(&host[off_grid_cells + 2 * c + 1], &meta, sizeof(meta));
+        }
         memcpy(&host[off_grid_items], grid.items.data(), grid.items.size() * sizeof(int));
         for (int k = 0; k < 3; k++) {
             ds.grid_lo[k] = grid.lo[k];
@@ -699,6 +706,13 @@ static int build_scene_blob(tcrt_ctx* ctx, const tcrt_scene* s) {
             ds.grid_dims[k] = grid.dims[k];
         }
         ds.grid_margin = grid.reg_margin;
+        // the far-origin test without fatten()'s square root: m(k2) = (sqrt(rmin^2 + k2 E) - rmin) 1.001 + 1e-6 rmin grows
+        // with k2, so m <= margin is a bound on k2 (solved in double, 0.1 % below: fewer rays on the grid is always sound)
+        {
+            const double rmin = ds.bvh_rmin, t = ((double)grid.reg_margin - 1e-6 * rmin) / 1.001;
+            const double k2 = t > 0.0 ? (t * t + 2.0 * t * rmin) / (double)TCRT_SPH_E : 0.0;
+            ds.grid_k2_max = (float)(0.999 * k2);
+        }
     }
 
     // into the pinned staging buffer (once every device has finished reading the previous scene out of it)
@@ -752,7 +766,7 @@ static int send_scene(tcrt_ctx* ctx, const tcrt_camera* cam) {
         d.ds.obj_info = nullptr;
         d.ds.bvh_sph = ctx->scene_bvh_s ? d.scene_mem + ctx->scene_off[5] : nullptr;
         d.ds.bvh_fin = ctx->scene_bvh_f ? d.scene_mem + ctx->scene_off[6] : nullptr;
-        d.ds.grid_cells = ctx->scene_grid ? reinterpret_cast<const int*>(d.scene_mem + ctx->scene_off[7]) : nullptr;
+        d.ds.grid_cells = ctx->scene_grid ? d.scene_mem + ctx->scene_off[7] : nullptr;
         d.ds.grid_items = ctx->scene_grid ? reinterpret_cast<const int*>(d.scene_mem + ctx->scene_off[8]) : nullptr;
     }
     ctx->cam = *cam;

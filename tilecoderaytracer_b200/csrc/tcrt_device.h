@@ -55,11 +55,14 @@ struct DeviceScene {
     int bvh_sph_root, bvh_fin_root;   // encoded like a child reference
     // optional uniform grid over the BVH-covered spheres (nullptr = none): a 3D-DDA finds the cells a ray crosses,
     // the spheres registered in a cell are tested exactly.  Rays fattened by more than grid_margin use the BVH.
-    const int* grid_cells;            // cell -> first item; n_cells + 1 entries
-    const int* grid_items;            // sphere slots
+    const float4* grid_cells;         // 2 per cell: (geometry of the cell's first sphere) (count, slot of the first sphere,
+                                      // position of the second one in grid_items, -) — the usual cell holds one sphere and
+                                      // costs ONE round of loads
+    const int* grid_items;            // sphere slots, cell after cell
     float grid_lo[3], grid_cell[3], grid_inv_cell[3];
     int grid_dims[3];
     float grid_margin;
+    float grid_k2_max;                // fatten().m <= grid_margin  <=>  its k2 <= grid_k2_max (m grows with k2)
     // per-ray fattening of the boxes (tcrt_render.cu `fatten`): bounding sphere (centre, radius^2)
     // of everything inside the BVHs, smallest BVH sphere radius, largest |coordinate|
     float bvh_cx, bvh_cy, bvh_cz, bvh_r2, bvh_rmin, bvh_cmax;
@@ -73,6 +76,10 @@ struct DeviceScene {
 int tcrt_build_bvh(const std::vector<float>& boxes, int n, std::vector<int>& order, std::vector<float4>& nodes,
                    int* depth);   // *depth: deepest node; the kernel's traversal stack holds TCRT_BVH_STACK entries
 #define TCRT_BVH_STACK 48
+// E = TCRT_SPH_E * 2(|O - Cs|^2 + Rs^2) bounds the rounding of the reference's sphere discriminant (`fatten`,
+// tcrt_render_common.cuh); the host derives the grid's far-origin bound from the same constant
+#define TCRT_SPH_E 4e-6f
+
 // host builder of the uniform grid over the BVH-covered spheres (tcrt_bvh.cpp)
 struct TcrtSphereGrid {
     float lo[3] = {0, 0, 0};

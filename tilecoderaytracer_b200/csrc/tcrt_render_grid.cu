@@ -132,8 +132,9 @@ __global__ void __launch_bounds__(kBlock, kGridMinBlocks) render_grid_kernel(con
             if (__any_sync(kFull, want)) {
                 if (want) task_linear<FM>(sm, sc, rO, rD, !any, best, bkey, found);
                 bool walking = want && !found;
-                const float m = fatten(sc, rO, true).m;
-                const bool far_origin = walking && !(m <= sc.grid_margin);          // also NaN
+                // far origin: fatten().m > grid_margin, as a bound on fatten's k2 (no square root; NaN counts as far)
+                const V3 dc = mk(rO.x - sc.bvh_cx, rO.y - sc.bvh_cy, rO.z - sc.bvh_cz);
+                const bool far_origin = walking && !(2.0f * (dot(dc, dc) + sc.bvh_r2) <= sc.grid_k2_max);
                 if (__any_sync(kFull, far_origin)) {
                     if (any ? bvh_fallback<true>(sc.bvh_sph, sc.bvh_sph_root, sm, sc, rO, rD, far_origin, &best, &bkey)
                             : bvh_fallback<false>(sc.bvh_sph, sc.bvh_sph_root, sm, sc, rO, rD, far_origin, &best, &bkey))
@@ -164,36 +165,40 @@ __global__ void __launch_bounds__(kBlock, kGridMinBlocks) render_grid_kernel(con
                     tmy = (sc.grid_lo[1] + sc.grid_cell[1] * (float)(cy + (sy > 0 ? 1 : 0)) - rO.y) * iy;
                     tmz = (sc.grid_lo[2] + sc.grid_cell[2] * (float)(cz + (sz > 0 ? 1 : 0)) - rO.z) * iz;
                 }
-                while (__any_sync(kFull, walking)) {
-                    if (walking) {
-                        const int c = cx + sc.grid_dims[0] * (cy + sc.grid_dims[1] * cz);
-                        TCRT_CHECK(c >= 0 && c < sc.grid_dims[0] * sc.grid_dims[1] * sc.grid_dims[2], kChkNode);
-                        const int j0 = __ldg(sc.grid_cells + c), j1 = __ldg(sc.grid_cells + c + 1);
-                        TCRT_UNROLL_LOOP
-                        for (int j = j0; j < j1; ++j) {
-                            const int i = __ldg(sc.grid_items + j);
-                            TCRT_CHECK(i >= 0 && i < sc.n_sph_bvh, kChkLeaf);
-                            task_sphere(sm, __ldg(sc.blob + i), i, rO, rD, !any, best, bkey, found);
+                // stop once the cell ends beyond `lim`: the light (shadow pass), or the best hit, which then lies inside the
+                // part of the ray already visited; the 2e-4 relative + absolute slack is 100x the DDA's own rounding
+                // (DESIGN.md §4.5).  A lane that has stopped waits at the loop's reconvergence point.
+                while (walking) {
+                    const int c = cx + sc.grid_dims[0] * (cy + sc.grid_dims[1] * cz);
+                    TCRT_CHECK(c >= 0 && c < sc.grid_dims[0] * sc.grid_dims[1] * sc.grid_dims[2], kChkNode);
+                    // the cell's record carries its first sphere: one round of loads for the usual one-sphere cell
+                    float4 g = __ldg(sc.grid_cells + 2 * c);
+                    const float4 meta = __ldg(sc.grid_cells + 2 * c + 1);
+                    int left = __float_as_int(meta.x), i = __float_as_int(meta.y), j = __float_as_int(meta.z);
+                    TCRT_UNROLL_LOOP
+                    while (left > 0) {
+                        TCRT_CHECK(i >= 0 && i < sc.n_sph_bvh, kChkLeaf);
+                        task_sphere(sm, g, i, rO, rD, !any, best, bkey, found);
+                        if (--left > 0) {
+                            i = __ldg(sc.grid_items + j++);
+                            g = __ldg(sc.blob + i);
                         }
-                        const float t_out = fminf(fminf(tmx, tmy), tmz);
-                        const float slack = 1e-4f * (1.0f + fabsf(t_out));
-                        // stop: a blocker is found / the cell ends beyond the light; the best hit lies inside the part of the
-                        // ray already visited (grid_traverse in tcrt_render_common.cuh has the argument)
-                        if (any ? (found || t_out - slack > best) : (best < t_out - slack)) {
-                            walking = false;
-                        } else if (tmx <= tmy && tmx <= tmz) {
-                            cx += sx;
-                            tmx += dtx;
-                            walking = (unsigned)cx < (unsigned)sc.grid_dims[0];
-                        } else if (tmy <= tmz) {
-                            cy += sy;
-                            tmy += dty;
-                            walking = (unsigned)cy < (unsigned)sc.grid_dims[1];
-                        } else {
-                            cz += sz;
-                            tmz += dtz;
-                            walking = (unsigned)cz < (unsigned)sc.grid_dims[2];
-                        }
+                    }
+                    const float t_out = fminf(fminf(tmx, tmy), tmz);
+                    if (found || t_out > best * 1.0002f + 2e-4f) {
+                        walking = false;
+                    } else if (tmx <= tmy && tmx <= tmz) {
+                        cx += sx;
+                        tmx += dtx;
+                        walking = (unsigned)cx < (unsigned)sc.grid_dims[0];
+                    } else if (tmy <= tmz) {
+                        cy += sy;
+                        tmy += dty;
+                        walking = (unsigned)cy < (unsigned)sc.grid_dims[1];
+                    } else {
+                        cz += sz;
+                        tmz += dtz;
+                        walking = (unsigned)cz < (unsigned)sc.grid_dims[2];
                     }
                 }
             }
