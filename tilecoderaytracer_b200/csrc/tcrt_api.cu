@@ -694,8 +694,9 @@ static int build_scene_blob(tcrt_ctx* ctx, const tcrt_scene* s) {
         // cell record: the first sphere's geometry next to the cell's count, so a one-sphere cell is one round of loads
         for (size_t c = 0; c < n_grid_cells; c++) {
             const int j0 = grid.cell_start[c], cnt = grid.cell_start[c + 1] - j0;
-            int4 meta = make_int4(cnt, cnt > 0 ? grid.items[j0] : 0, j0 + 1, 0);
-            if (cnt > 0) host[off_grid_cells + 2 * c] = host[grid.items[j0]];     // spheres sit at the front of the blob
+            int4 meta = make_int4(cnt > 0 ? cnt - 1 : 0, cnt > 0 ? grid.items[j0] : 0, j0 + 1, 0);
+            // spheres sit at the front of the blob; an empty cell gets a sphere whose discriminant is negative for every ray
+            host[off_grid_cells + 2 * c] = cnt > 0 ? host[grid.items[j0]] : make_float4(0.f, 0.f, 0.f, -1e30f);
             memcpy(&host[off_grid_cells + 2 * c + 1], &meta, sizeof(meta));
         }
         memcpy(&host[off_grid_items], grid.items.data(), grid.items.size() * sizeof(int));

@@ -55,9 +55,9 @@ struct DeviceScene {
     int bvh_sph_root, bvh_fin_root;   // encoded like a child reference
     // optional uniform grid over the BVH-covered spheres (nullptr = none): a 3D-DDA finds the cells a ray crosses,
     // the spheres registered in a cell are tested exactly.  Rays fattened by more than grid_margin use the BVH.
-    const float4* grid_cells;         // 2 per cell: (geometry of the cell's first sphere) (count, slot of the first sphere,
-                                      // position of the second one in grid_items, -) — the usual cell holds one sphere and
-                                      // costs ONE round of loads
+    const float4* grid_cells;         // 2 per cell: (geometry of the cell's first sphere; r^2 = -1e30 in an empty cell: never
+                                      // hit) (number of FURTHER spheres, slot of the first sphere, position of the second one
+                                      // in grid_items, -) — the usual cell holds one sphere and costs ONE round of loads
     const int* grid_items;            // sphere slots, cell after cell
     float grid_lo[3], grid_cell[3], grid_inv_cell[3];
     int grid_dims[3];

@@ -171,18 +171,19 @@ __global__ void __launch_bounds__(kBlock, kGridMinBlocks) render_grid_kernel(con
                 while (walking) {
                     const int c = cx + sc.grid_dims[0] * (cy + sc.grid_dims[1] * cz);
                     TCRT_CHECK(c >= 0 && c < sc.grid_dims[0] * sc.grid_dims[1] * sc.grid_dims[2], kChkNode);
-                    // the cell's record carries its first sphere: one round of loads for the usual one-sphere cell
+                    // the cell's record carries its first sphere (an empty cell one that no ray can hit): the test starts on
+                    // ONE round of loads, the second half of the record is needed on a hit and for the cell's other spheres
                     float4 g = __ldg(sc.grid_cells + 2 * c);
                     const float4 meta = __ldg(sc.grid_cells + 2 * c + 1);
-                    int left = __float_as_int(meta.x), i = __float_as_int(meta.y), j = __float_as_int(meta.z);
+                    int more = __float_as_int(meta.x), i = __float_as_int(meta.y), j = __float_as_int(meta.z);
                     TCRT_UNROLL_LOOP
-                    while (left > 0) {
+                    for (;;) {
                         TCRT_CHECK(i >= 0 && i < sc.n_sph_bvh, kChkLeaf);
                         task_sphere(sm, g, i, rO, rD, !any, best, bkey, found);
-                        if (--left > 0) {
-                            i = __ldg(sc.grid_items + j++);
-                            g = __ldg(sc.blob + i);
-                        }
+                        if (more <= 0) break;
+                        --more;
+                        i = __ldg(sc.grid_items + j++);
+                        g = __ldg(sc.blob + i);
                     }
                     const float t_out = fminf(fminf(tmx, tmy), tmz);
                     if (found || t_out > best * 1.0002f + 2e-4f) {
