@@ -703,6 +703,7 @@ static int build_scene_blob(tcrt_ctx* ctx, const tcrt_scene* s) {
         for (int k = 0; k < 3; k++) {
             ds.grid_lo[k] = grid.lo[k];
             ds.grid_cell[k] = grid.cell[k];
+            ds.grid_hi[k] = grid.lo[k] + grid.cell[k] * (float)grid.dims[k];
             ds.grid_inv_cell[k] = 1.0f / grid.cell[k];
             ds.grid_dims[k] = grid.dims[k];
         }

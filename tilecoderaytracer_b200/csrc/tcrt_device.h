@@ -59,7 +59,7 @@ struct DeviceScene {
                                       // hit) (number of FURTHER spheres, slot of the first sphere, position of the second one
                                       // in grid_items, -) — the usual cell holds one sphere and costs ONE round of loads
     const int* grid_items;            // sphere slots, cell after cell
-    float grid_lo[3], grid_cell[3], grid_inv_cell[3];
+    float grid_lo[3], grid_hi[3], grid_cell[3], grid_inv_cell[3];   // hi = lo + cell * dims
     int grid_dims[3];
     float grid_margin;
     float grid_k2_max;                // fatten().m <= grid_margin  <=>  its k2 <= grid_k2_max (m grows with k2)

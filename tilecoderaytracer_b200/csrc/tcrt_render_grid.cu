@@ -145,9 +145,9 @@ __global__ void __launch_bounds__(kBlock, kGridMinBlocks) render_grid_kernel(con
                 const float ix = rcp_approx(fabsf(rD.x) < 1e-30f ? copysignf(1e-30f, rD.x) : rD.x);
                 const float iy = rcp_approx(fabsf(rD.y) < 1e-30f ? copysignf(1e-30f, rD.y) : rD.y);
                 const float iz = rcp_approx(fabsf(rD.z) < 1e-30f ? copysignf(1e-30f, rD.z) : rD.z);
-                const float ax = (sc.grid_lo[0] - rO.x) * ix, bx = (sc.grid_lo[0] + sc.grid_cell[0] * (float)sc.grid_dims[0] - rO.x) * ix;
-                const float ay = (sc.grid_lo[1] - rO.y) * iy, by = (sc.grid_lo[1] + sc.grid_cell[1] * (float)sc.grid_dims[1] - rO.y) * iy;
-                const float az = (sc.grid_lo[2] - rO.z) * iz, bz = (sc.grid_lo[2] + sc.grid_cell[2] * (float)sc.grid_dims[2] - rO.z) * iz;
+                const float ax = (sc.grid_lo[0] - rO.x) * ix, bx = (sc.grid_hi[0] - rO.x) * ix;
+                const float ay = (sc.grid_lo[1] - rO.y) * iy, by = (sc.grid_hi[1] - rO.y) * iy;
+                const float az = (sc.grid_lo[2] - rO.z) * iz, bz = (sc.grid_hi[2] - rO.z) * iz;
                 const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
                 const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
                 const float t0 = fmaxf(tn, 0.0f);
@@ -173,8 +173,9 @@ __global__ void __launch_bounds__(kBlock, kGridMinBlocks) render_grid_kernel(con
                     TCRT_CHECK(c >= 0 && c < sc.grid_dims[0] * sc.grid_dims[1] * sc.grid_dims[2], kChkNode);
                     // the cell's record carries its first sphere (an empty cell one that no ray can hit): the test starts on
                     // ONE round of loads, the second half of the record is needed on a hit and for the cell's other spheres
-                    float4 g = __ldg(sc.grid_cells + 2 * c);
-                    const float4 meta = __ldg(sc.grid_cells + 2 * c + 1);
+                    const float4* rec = reinterpret_cast<const float4*>(reinterpret_cast<const char*>(sc.grid_cells) + 32u * (unsigned)c);
+                    float4 g = __ldg(rec);
+                    const float4 meta = __ldg(rec + 1);
                     int more = __float_as_int(meta.x), i = __float_as_int(meta.y), j = __float_as_int(meta.z);
                     TCRT_UNROLL_LOOP
                     for (;;) {
