@@ -20,16 +20,20 @@ namespace {
 #ifndef TCRT_GRID_MIN_BLOCKS
 #define TCRT_GRID_MIN_BLOCKS 4
 #endif
+#ifndef TCRT_GRID_BLOCK
+#define TCRT_GRID_BLOCK 256
+#endif
+constexpr int kGridBlock = TCRT_GRID_BLOCK;
 constexpr int kGridMinBlocks = TCRT_GRID_MIN_BLOCKS;      // the walk waits on cell and sphere loads: 4 CTAs/SM at 64 registers
 
 template <int CAP, int FM>
-__global__ void __launch_bounds__(kBlock, kGridMinBlocks) render_grid_kernel(const __grid_constant__ RenderLaunch rl) {
+__global__ void __launch_bounds__(kGridBlock, kGridMinBlocks) render_grid_kernel(const __grid_constant__ RenderLaunch rl) {
     extern __shared__ float4 smem4[];
     const DeviceScene& sc = rl.scene;
     // ---- stage the sweep blob (the grid-covered spheres in front of stage_off stay in global memory) ----------------
     const int stage_off = sc.stage_off;
     const int n_stage = sc.blob_f4 - stage_off;
-    for (int i = threadIdx.x; i < n_stage; i += kBlock) smem4[i] = __ldg(sc.blob + stage_off + i);
+    for (int i = threadIdx.x; i < n_stage; i += kGridBlock) smem4[i] = __ldg(sc.blob + stage_off + i);
     __syncthreads();
     Sm sm;
     const float4* base = smem4 - stage_off;
@@ -96,6 +100,9 @@ __global__ void __launch_bounds__(kBlock, kGridMinBlocks) render_grid_kernel(con
         float diffuse = 0.f, specular = 0.f, kref = 0.f, inten = 0.f;
         bool is_light = false, hit = false, shade = false;
         V3 local = mk(0.f, 0.f, 0.f);
+#ifdef TCRT_LANE_STATS
+        int st_prev = 0, st_sum = 0, st_maxsum = 0;
+#endif
 #pragma unroll 1
         for (int pass = 0; pass <= sc.n_lights; ++pass) {
             const bool any = pass > 0;                    // warp-uniform: nearest-hit or any-hit walk
@@ -168,7 +175,13 @@ __global__ void __launch_bounds__(kBlock, kGridMinBlocks) render_grid_kernel(con
                 // stop once the cell ends beyond `lim`: the light (shadow pass), or the best hit, which then lies inside the
                 // part of the ray already visited; the 2e-4 relative + absolute slack is 100x the DDA's own rounding
                 // (DESIGN.md §4.5).  A lane that has stopped waits at the loop's reconvergence point.
+#ifdef TCRT_LANE_STATS
+                int st_len = 0;
+#endif
                 while (walking) {
+#ifdef TCRT_LANE_STATS
+                    ++st_len;
+#endif
                     const int c = cx + sc.grid_dims[0] * (cy + sc.grid_dims[1] * cz);
                     TCRT_CHECK(c >= 0 && c < sc.grid_dims[0] * sc.grid_dims[1] * sc.grid_dims[2], kChkNode);
                     // the cell's record carries its first sphere (an empty cell one that no ray can hit): the test starts on
@@ -203,6 +216,21 @@ __global__ void __launch_bounds__(kBlock, kGridMinBlocks) render_grid_kernel(con
                         walking = (unsigned)cz < (unsigned)sc.grid_dims[2];
                     }
                 }
+#ifdef TCRT_LANE_STATS
+                {   // slots: 0/1 nearest walks (warp steps, lane steps); 2/3 shadow walks; 4/5 per bounce: sum of the shadow
+                    // passes' longest walks / longest per-lane SUM of shadow walks (what fusing the passes would take)
+                    const int mx = __reduce_max_sync(kFull, st_len), tot = __reduce_add_sync(kFull, st_len);
+                    if (lane == 0) {
+                        atomicAdd(&g_lane_stats[any ? 2 : 0], (unsigned long long)mx);
+                        atomicAdd(&g_lane_stats[any ? 3 : 1], (unsigned long long)tot);
+                    }
+                    if (any) {
+                        st_prev += st_len;
+                        st_sum += mx;
+                        st_maxsum = __reduce_max_sync(kFull, st_prev);
+                    }
+                }
+#endif
             }
             if (!any) {
                 // ---- winner's hit record (CollisionObject ctor, SceneObject.h:47-105) ----------------------------------------
@@ -297,6 +325,12 @@ __global__ void __launch_bounds__(kBlock, kGridMinBlocks) render_grid_kernel(con
             }
         }
 
+#ifdef TCRT_LANE_STATS
+        if (lane == 0) {
+            atomicAdd(&g_lane_stats[4], (unsigned long long)st_sum);
+            atomicAdd(&g_lane_stats[5], (unsigned long long)st_maxsum);
+        }
+#endif
         // ---- continue or finish the path --------------------------------------------------------
         bool reflected = false;
         if (active) {
@@ -369,7 +403,7 @@ template <int CAP, int FM>
 cudaError_t launch_grid_one(const RenderLaunch& rl, int grid, size_t smem, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(render_grid_kernel<CAP, FM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    render_grid_kernel<CAP, FM><<<grid, kBlock, smem, stream>>>(rl);
+    render_grid_kernel<CAP, FM><<<grid, kGridBlock, smem, stream>>>(rl);
     return cudaGetLastError();
 }
 
@@ -379,6 +413,18 @@ cudaError_t launch_grid_cap(const RenderLaunch& rl, int fm, int grid, size_t sme
 }
 
 }  // namespace
+
+#ifdef TCRT_LANE_STATS
+extern "C" int tcrt_dev_lane_stats_grid(unsigned long long* out16, int reset) {
+    cudaDeviceSynchronize();
+    if (out16 && cudaMemcpyFromSymbol(out16, g_lane_stats, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+    if (reset) {
+        unsigned long long z[16] = {};
+        if (cudaMemcpyToSymbol(g_lane_stats, z, sizeof z) != cudaSuccess) return -1;
+    }
+    return 0;
+}
+#endif
 
 // fm: 0 no finite planes, 3 a handful swept linearly; rl.scene.grid_cells != nullptr (tcrt_upload_scene built a grid)
 cudaError_t tcrt_launch_render_grid(const RenderLaunch& rl, int fm, int sm_count, size_t smem, cudaStream_t stream) {

@@ -20,6 +20,8 @@ if "--pool" in sys.argv:
     NAMES = {0: "iterations", 2: "pool: inner-node steps", 4: "pool: leaf phases", 6: "pool: fetch events (free lanes)",
              8: "pool: inner steps, lanes blocked on leaves", 12: "pool: inner steps, lanes without task",
              10: "pool calls (light-A tasks)"}
+if "--grid" in sys.argv:
+    NAMES = {0: "nearest walks: DDA steps", 2: "shadow walks: DDA steps"}
 ctx = api.Context([0])
 for name in [a for a in sys.argv[1:] if not a.startswith("--")] or ["synth256_1080p_d10"]:
     scene_name, w, h, d = WORKLOADS[name]
@@ -29,7 +31,7 @@ for name in [a for a in sys.argv[1:] if not a.startswith("--")] or ["synth256_10
     p = api.default_params(w, h, d)
     ctx.render_device(p)
     out = (C.c_ulonglong * 16)()
-    fn = lib.tcrt_dev_lane_stats_pool if "--pool" in sys.argv else (lib.tcrt_dev_lane_stats_wave if "--wave" in sys.argv else lib.tcrt_dev_lane_stats)
+    fn = lib.tcrt_dev_lane_stats_grid if "--grid" in sys.argv else lib.tcrt_dev_lane_stats_pool if "--pool" in sys.argv else (lib.tcrt_dev_lane_stats_wave if "--wave" in sys.argv else lib.tcrt_dev_lane_stats)
     fn(out, 1)
     st = ctx.render_device(p)
     fn(out, 0)
@@ -38,3 +40,6 @@ for name in [a for a in sys.argv[1:] if not a.startswith("--")] or ["synth256_10
         n, lanes = out[k], out[k + 1]
         if n:
             print(f"  {label:28s} warp-steps {n:12d}  lanes/step {lanes / n:5.2f}")
+    if "--grid" in sys.argv:
+        print(f"  shadow walks of a bounce: sum over passes of the longest walk {out[4]}, longest per-lane sum {out[5]} "
+              f"({out[5] / max(out[4], 1):.3f})")
