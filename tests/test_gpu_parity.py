@@ -728,3 +728,31 @@ def test_sphere_grid_edge_cases(gpu_ctx, case):
     want, cnt = O.render(s.flatten(), c, p)
     assert_bit_identical(img, want, f"sphere grid: {case}")
     check_counters(stats, cnt)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,w,h,d", [("synth256", 1920, 1080, 10), ("default", 3840, 2160, 50), ("default", 1920, 1080, 5)])
+def test_chunked_host_render_equals_single_launch(gpu_ctx, name, w, h, d):
+    """A band that goes to host memory is rendered as column chunks, their launches round robin on several streams
+    with the copies behind them (render_submit); a band that stays on the device is one launch.  Same frame, same
+    ray counters — into pinned and into pageable memory, and with two such frames in flight."""
+    scene, cam = make_scene(name)
+    p = api.default_params(w, h, d)
+    gpu_ctx.upload(scene, cam)
+    st_dev = gpu_ctx.render_device(p)
+    want = gpu_ctx.download(np.empty((w, h, 3), np.float32)).copy()
+    assert st_dev.gpu_launches == 1
+    hb = [api.HostBuffer(w * h * 12) for _ in range(2)]
+    outs = [b.array(np.float32, (w, h, 3)) for b in hb]
+    outs[0][:] = -1.0
+    img, st = gpu_ctx.render(p, out=outs[0])
+    assert st.gpu_launches > 1, "expected a chunked render"
+    assert np.array_equal(bits(img), bits(want)) and st.rays == st_dev.rays
+    img2, st2 = gpu_ctx.render(p)          # pageable numpy memory
+    assert np.array_equal(bits(img2), bits(want)) and st2.rays == st_dev.rays
+    for o in outs:
+        o[:] = -1.0
+    tickets = [gpu_ctx.render_async(p, out=o) for o in outs]
+    for t, o in zip(tickets, outs):
+        assert gpu_ctx.wait(t).rays == st_dev.rays
+        assert np.array_equal(bits(o), bits(want))

@@ -30,23 +30,28 @@ namespace {
 
 // What one frame in flight owns on a device.  Two sets per device: tcrt_render_async renders frame n+1 into one
 // while frame n's band is still being copied out of the other.
+constexpr int kMaxChunks = 16;     // column chunks of a band that goes to host memory (= events per frame)
+constexpr int kChunkStreams = 4;   // streams their launches alternate on
+
 struct FrameRes {
     float* frame = nullptr;                   // the band, (x1-x0)*height*3 floats, x-major
     size_t frame_cap = 0;                     // floats
     int x0 = 0, x1 = 0, height = 0;
-    unsigned char* ctl = nullptr;             // 64 B: queue head @0, counters @8..31
+    unsigned char* ctl = nullptr;             // queue head @0, ray counters @8..31, queue heads of the column chunks @64 (kMaxChunks x u32)
     unsigned long long* h_counters = nullptr; // pinned, 4 x u64 (slot 0 unused)
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;   // around the kernels (render stream)
     cudaEvent_t ev_done = nullptr;            // ray counters are in h_counters (render stream)
     cudaEvent_t ev_c1 = nullptr;              // last chunk is in host memory (copy stream)
-    cudaEvent_t ev_chunk[8] = {};             // chunk k rendered
+    cudaEvent_t ev_chunk[kMaxChunks] = {};            // chunk k rendered
+    cudaEvent_t ev_start = nullptr;           // control block zeroed, row order uploaded (render stream)
 };
 
 struct DeviceState {
     int dev = -1;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t copy_stream = nullptr;           // D2H of finished column chunks, behind the render stream
+    cudaStream_t chunk_stream[kChunkStreams - 1] = {};   // with `stream`: the column chunks of a band that goes to host memory, round robin (render_submit)
+    cudaStream_t copy_stream = nullptr;           // D2H of finished column chunks, behind the render streams
     // scene
     float4* scene_mem = nullptr;
     size_t scene_cap_f4 = 0;
@@ -103,6 +108,7 @@ struct tcrt_ctx {
     std::vector<double> col_costs, row_costs;
     tcrt_params cost_params{};
     bool costs_valid = false;
+    bool one_stream = false;               // developer builds: the chunk launches of a band on one stream, as before round 2
     unsigned long long cost_serial = 0;    // bumped by every new cost map
     char* host_text = nullptr;   // pinned staging for tcrt_write_txt
     size_t host_text_cap = 0;
@@ -164,12 +170,15 @@ void free_device(DeviceState& d) {
     if (d.dev < 0) return;
     cudaSetDevice(d.dev);
     if (d.stream) cudaStreamSynchronize(d.stream);
+    for (auto& cs : d.chunk_stream)
+        if (cs) cudaStreamSynchronize(cs);
     if (d.copy_stream) cudaStreamSynchronize(d.copy_stream);
     cudaFree(d.scene_mem);
     for (FrameRes& f : d.res) {
         cudaFree(f.frame);
         cudaFree(f.ctl);
         cudaFreeHost(f.h_counters);
+        if (f.ev_start) cudaEventDestroy(f.ev_start);
         if (f.ev_k0) cudaEventDestroy(f.ev_k0);
         if (f.ev_k1) cudaEventDestroy(f.ev_k1);
         if (f.ev_c1) cudaEventDestroy(f.ev_c1);
@@ -190,6 +199,8 @@ void free_device(DeviceState& d) {
     cudaFreeHost(d.txt_stage);
     for (auto& e : d.ev_txt)
         if (e) cudaEventDestroy(e);
+    for (auto& cs : d.chunk_stream)
+        if (cs) cudaStreamDestroy(cs);
     if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
     if (d.stream) cudaStreamDestroy(d.stream);
     d = DeviceState{};
@@ -308,6 +319,9 @@ int tcrt_create(tcrt_ctx** out, const int* device_ids, int n_devices) {
     int avail = tcrt_device_count();
     if (avail <= 0) return fail(nullptr, TCRT_ERR_NO_DEVICE, "no CUDA device available (%s)", g_err.c_str());
     tcrt_ctx* ctx = new tcrt_ctx();
+#ifdef TCRT_DEV_KNOBS   // developer build only (A/B timing); the product never reads the environment
+    ctx->one_stream = getenv("TCRT_ONE_STREAM") != nullptr;
+#endif
     ctx->devs.resize(n_devices);
     for (int i = 0; i < n_devices; i++) {
         int dev = device_ids ? device_ids[i] : i;
@@ -327,15 +341,18 @@ int tcrt_create(tcrt_ctx** out, const int* device_ids, int n_devices) {
         }
         if (e == cudaSuccess) d.sm_count = prop.multiProcessorCount;
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
+        for (auto& cs : d.chunk_stream)
+            if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking);
         for (FrameRes& f : d.res) {
             for (auto& ev : f.ev_chunk)
                 if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f.ev_start, cudaEventDisableTiming);
             if (e == cudaSuccess) e = cudaEventCreate(&f.ev_k0);
             if (e == cudaSuccess) e = cudaEventCreate(&f.ev_k1);
             if (e == cudaSuccess) e = cudaEventCreate(&f.ev_c1);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f.ev_done, cudaEventDisableTiming);
-            if (e == cudaSuccess) e = cudaMalloc((void**)&f.ctl, 64);
+            if (e == cudaSuccess) e = cudaMalloc((void**)&f.ctl, 64 + kMaxChunks * sizeof(unsigned int));
             if (e == cudaSuccess) e = cudaHostAlloc((void**)&f.h_counters, 64, cudaHostAllocPortable);
         }
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d.ev_scene, cudaEventDisableTiming);
@@ -798,7 +815,8 @@ int tcrt_rebalance_columns(const int* bounds, const double* ms, int n_bands, int
 }
 
 static int launch_band(tcrt_ctx* ctx, DeviceState& d, const tcrt_params* p, int cx0, int cx1, unsigned int* col_cost,
-                       int* launches);
+                       int* launches, cudaStream_t stream = nullptr, unsigned int* queue = nullptr);
+static int ensure_row_order(tcrt_ctx* ctx, DeviceState& d, const tcrt_params* p, int cx0, int cx1, bool pre_pass, const int** out);
 
 // One frame = submit (everything is queued on the devices' streams, nothing waits) + finish (waits for this
 // frame's events only, reads its timings and ray counters).  `set` picks which of the two FrameRes sets of
@@ -853,38 +871,62 @@ static int render_submit(tcrt_ctx* ctx, const tcrt_params* p, int x0, int x1, fl
             int rc = ensure(ctx, d.fr().frame, d.fr().frame_cap, n_floats);
             if (rc) return rc;
             CK(ctx, cudaMemsetAsync(d.fr().ctl, 0, 64, d.stream));
-            // With a host destination the band is rendered as up to 8 column chunks; chunk k is copied
-            // back on the copy stream while chunk k+1 renders (the output is x-major: a chunk is one
-            // contiguous slice).  Without one, a single launch.
+            // With a host destination the band is rendered as up to kMaxChunks column chunks; chunk k is copied back on
+            // the copy stream while the next chunks render (the output is x-major: a chunk is one contiguous slice).
+            // The chunks are separate launches on kChunkStreams streams, round robin: a launch ends in a tail of half-empty
+            // SMs (its deepest paths: 0.13-0.25 ms per launch measured), and with the next chunks' launches already queued
+            // on the other streams their CTAs move in as this one's retire.  Without a host destination, a single launch.
             int n_chunks = 1;
             if (host_band) {
                 const long long px = (long long)(d.fr().x1 - d.fr().x0) * p->height;
                 const long long chunk_px = 512 * 1024;   // 128 K .. 512 K pixels per chunk measure the same
-                n_chunks = (int)std::min<long long>(std::min<long long>(8, d.fr().x1 - d.fr().x0), std::max<long long>(1, px / chunk_px));
+                n_chunks = (int)std::min<long long>(std::min<long long>(kMaxChunks, d.fr().x1 - d.fr().x0), std::max<long long>(1, px / chunk_px));
+            }
+            // chunk boundaries on tile boundaries, so that every chunk of a tileable band is tileable
+            auto chunk_start = [&](int j) {
+                const int w = d.fr().x1 - d.fr().x0;
+                int c = (int)((long long)w * j / n_chunks);
+                if (j < n_chunks && w % TCRT_TILE_W == 0) c -= c % TCRT_TILE_W;
+                return d.fr().x0 + c;
+            };
+            const bool two_streams = n_chunks > 1 && !ctx->one_stream;   // (several streams)
+            if (two_streams) {
+                // everything the launches on the second stream read must be in place: queue heads, counters, row order
+                CK(ctx, cudaMemsetAsync(d.fr().ctl + 64, 0, kMaxChunks * sizeof(unsigned int), d.stream));
+                const int* unused = nullptr;
+                rc = ensure_row_order(ctx, d, p, chunk_start(0), chunk_start(1), false, &unused);
+                if (rc) return rc;
+                CK(ctx, cudaEventRecord(d.fr().ev_start, d.stream));
+                for (auto& cs : d.chunk_stream) CK(ctx, cudaStreamWaitEvent(cs, d.fr().ev_start, 0));
             }
             CK(ctx, cudaEventRecord(d.fr().ev_k0, d.stream));
+            int last_on[kChunkStreams];
+            for (int& l : last_on) l = -1;
             for (int k = 0; k < n_chunks; k++) {
-                // chunk boundaries on tile boundaries, so that every chunk of a tileable band is tileable
-                auto chunk_start = [&](int j) {
-                    const int w = d.fr().x1 - d.fr().x0;
-                    int c = (int)((long long)w * j / n_chunks);
-                    if (j < n_chunks && w % TCRT_TILE_W == 0) c -= c % TCRT_TILE_W;
-                    return d.fr().x0 + c;
-                };
                 const int cx0 = chunk_start(k), cx1 = chunk_start(k + 1);
                 if (cx1 <= cx0) continue;
-                if (k > 0) CK(ctx, cudaMemsetAsync(d.fr().ctl, 0, 4, d.stream));   // queue head only; ray counters accumulate
-                rc = launch_band(ctx, d, p, cx0, cx1, nullptr, &launches);
+                cudaStream_t ks = d.stream;
+                if (two_streams) {
+                    const int si = k % kChunkStreams;
+                    if (si > 0) ks = d.chunk_stream[si - 1];
+                    last_on[si] = k;
+                    rc = launch_band(ctx, d, p, cx0, cx1, nullptr, &launches, ks, reinterpret_cast<unsigned int*>(d.fr().ctl + 64) + k);
+                } else {
+                    if (k > 0) CK(ctx, cudaMemsetAsync(d.fr().ctl, 0, 4, d.stream));   // queue head only; ray counters accumulate
+                    rc = launch_band(ctx, d, p, cx0, cx1, nullptr, &launches);
+                }
                 if (rc) return rc;
                 if (host_band) {
                     const size_t off = (size_t)(cx0 - d.fr().x0) * p->height * 3;
                     const size_t cnt = (size_t)(cx1 - cx0) * p->height * 3;
-                    CK(ctx, cudaEventRecord(d.fr().ev_chunk[k], d.stream));
+                    CK(ctx, cudaEventRecord(d.fr().ev_chunk[k], ks));
                     CK(ctx, cudaStreamWaitEvent(d.copy_stream, d.fr().ev_chunk[k], 0));
                     CK(ctx, cudaMemcpyAsync(host_band + (size_t)(d.fr().x0 - x0) * p->height * 3 + off, d.fr().frame + off,
                                             cnt * sizeof(float), cudaMemcpyDeviceToHost, d.copy_stream));
                 }
             }
+            for (int si = 1; si < kChunkStreams; si++)      // the frame ends on d.stream
+                if (last_on[si] >= 0) CK(ctx, cudaStreamWaitEvent(d.stream, d.fr().ev_chunk[last_on[si]], 0));
             CK(ctx, cudaEventRecord(d.fr().ev_k1, d.stream));
             CK(ctx, cudaMemcpyAsync(d.fr().h_counters, d.fr().ctl, 32, cudaMemcpyDeviceToHost, d.stream));
             CK(ctx, cudaEventRecord(d.fr().ev_done, d.stream));
@@ -975,7 +1017,8 @@ static int render_impl(tcrt_ctx* ctx, const tcrt_params* p, int x0, int x1, floa
 // Columns [cx0, cx1) of device d's band [d.fr().x0, d.fr().x1) of the frame `p`, into the band's frame buffer.
 // The caller has sized the buffer and zeroed the queue head.
 static int launch_band(tcrt_ctx* ctx, DeviceState& d, const tcrt_params* p, int cx0, int cx1, unsigned int* col_cost,
-                       int* launches) {
+                       int* launches, cudaStream_t stream, unsigned int* queue) {
+    if (!stream) stream = d.stream;
     RenderLaunch rl{};
     rl.scene = d.ds;
     rl.cam = ctx->cam;
@@ -992,16 +1035,33 @@ static int launch_band(tcrt_ctx* ctx, DeviceState& d, const tcrt_params* p, int 
     rl.far_dist = p->far_dist;
     rl.n_objects = ctx->n_objects;
     rl.out = d.fr().frame + (size_t)(cx0 - d.fr().x0) * p->height * 3;
-    rl.queue = reinterpret_cast<unsigned int*>(d.fr().ctl);
+    rl.queue = queue ? queue : reinterpret_cast<unsigned int*>(d.fr().ctl);
     rl.counters = reinterpret_cast<unsigned long long*>(d.fr().ctl + 8);
     rl.col_cost = col_cost;
-    // Longest-processing-time-first: with a cost map for this (scene, camera, params) — i.e. after
-    // tcrt_balance_columns — the queue runs row by row, the expensive rows first, so the tail of the
-    // launch is made of cheap pixels (sky, floor) instead of the deepest reflection paths, whose
-    // bounces are sequential and would otherwise drain on an almost empty GPU.
-    rl.row_order = nullptr;
+    int rc_ro = ensure_row_order(ctx, d, p, cx0, cx1, col_cost != nullptr, &rl.row_order);
+    if (rc_ro) return rc_ro;
+    // scratch of the wavefront path (large frames of sphere-BVH scenes): ray queues and per-path state of one chunk
+    const size_t wave_need = tcrt_wave_mem_needed(rl);
+    if (wave_need > d.wave_bytes) {
+        if (d.wave_mem) CK(ctx, cudaFree(d.wave_mem));
+        d.wave_mem = nullptr;
+        d.wave_bytes = 0;
+        CK(ctx, cudaMalloc(&d.wave_mem, wave_need));
+        d.wave_bytes = wave_need;
+    }
+    CK(ctx, tcrt_launch_render(rl, d.sm_count, stream, launches, d.wave_mem, d.wave_bytes));
+    return TCRT_OK;
+}
+
+// Longest-processing-time-first: with a cost map for this (scene, camera, params) — i.e. after
+// tcrt_balance_columns — the queue runs row by row, the expensive rows first, so the tail of the
+// launch is made of cheap pixels (sky, floor) instead of the deepest reflection paths, whose
+// bounces are sequential and would otherwise drain on an almost empty GPU.  *out = the device's row order for a
+// launch over columns [cx0, cx1) (uploaded on d.stream when it is not there yet), or nullptr.
+static int ensure_row_order(tcrt_ctx* ctx, DeviceState& d, const tcrt_params* p, int cx0, int cx1, bool pre_pass, const int** out) {
+    *out = nullptr;
     const tcrt_params& cp = ctx->cost_params;
-    if (ctx->costs_valid && !col_cost && p->height > 1 && cp.width == p->width && cp.height == p->height &&
+    if (ctx->costs_valid && !pre_pass && p->height > 1 && cp.width == p->width && cp.height == p->height &&
         cp.max_depth == p->max_depth && cp.shadows_on == p->shadows_on && cp.reflections_on == p->reflections_on) {
         // rows, or 8-row tile rows when the launch is tiled (same rule as tcrt_launch_render)
         const bool tiled = (cx1 - cx0) % TCRT_TILE_W == 0 && p->height % TCRT_TILE_H == 0;
@@ -1024,18 +1084,8 @@ static int launch_band(tcrt_ctx* ctx, DeviceState& d, const tcrt_params* p, int 
             d.row_order_serial = ctx->cost_serial;
             d.row_order_h = key_h;
         }
-        rl.row_order = d.row_order;
+        *out = d.row_order;
     }
-    // scratch of the wavefront path (large frames of sphere-BVH scenes): ray queues and per-path state of one chunk
-    const size_t wave_need = tcrt_wave_mem_needed(rl);
-    if (wave_need > d.wave_bytes) {
-        if (d.wave_mem) CK(ctx, cudaFree(d.wave_mem));
-        d.wave_mem = nullptr;
-        d.wave_bytes = 0;
-        CK(ctx, cudaMalloc(&d.wave_mem, wave_need));
-        d.wave_bytes = wave_need;
-    }
-    CK(ctx, tcrt_launch_render(rl, d.sm_count, d.stream, launches, d.wave_mem, d.wave_bytes));
     return TCRT_OK;
 }
 
