@@ -516,6 +516,16 @@ def run_workload(ctx, dist, args, name, steps, warmup, inproc, sample_clocks=Fal
     return res
 
 
+def _num(v):
+    """Leading number of an exported ncu value ("78.03 %" -> 78.03); None when absent."""
+    if v is None:
+        return None
+    try:
+        return float(str(v).split()[0].replace(",", ""))
+    except ValueError:
+        return None
+
+
 def fractions(name, res, peak):
     """frac_executed / frac_algorithmic of one measured workload (rank 0)."""
     scene_name, w, h, depth = WORKLOADS[name]
@@ -741,6 +751,12 @@ def run_ours(args):
                     "ncu capture named in `capture`, x this run's rays / this run's kernel time) / peak.  frac_algorithmic = flops of the "
                     "reference's linear sweep over every object for these rays / the same peak: a speed-up over the linear sweep "
                     "(BVH and box clusters skip most of it), not a fraction of the machine",
+            # what the FP32 fraction leaves out: how busy the issue ports are and how many lanes an instruction carries
+            # (same committed capture; a divergent kernel is bound by these, not by the FP32 pipe)
+            "capture_issue_slot_pct": _num(m.get("smsp__issue_active.avg.pct_of_peak_sustained_active")),
+            "capture_threads_per_inst": _num(m.get("smsp__thread_inst_executed_per_inst_executed.ratio")),
+            "capture_fma_pipe_inst_pct": _num(m.get("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active")),
+            "capture_icache_hit_pct": _num(m.get("sm__icc_request_hit_rate.pct")),
             "hbm_algorithmic_bytes_per_launch": band_bytes,
             "hbm_frac_of_measured": (band_bytes / kernel_s / 1e9) / measured_hbm_gbs(),
         }
