@@ -168,6 +168,10 @@ int tcrt_upload_scene(tcrt_ctx* ctx, const tcrt_scene* scene, const tcrt_camera*
  * planes in their BVH, [3] box clusters, [4] rectangles owned by clusters, [5] spheres swept linearly, [6] finite planes
  * swept linearly, [7] bytes of scene staged into shared memory per CTA. */
 int tcrt_scene_structures(tcrt_ctx* ctx, int info[8]);
+/* The same decision for a scene that has not been uploaded — host work only, no device needed (sort, box clusters, BVHs,
+ * grid; what tcrt_upload_scene does before its copy).  grid_dims (optional): cells per axis of the sphere grid, 0 0 0
+ * without one.  TCRT_ERR_UNSUPPORTED for a scene tcrt_upload_scene would refuse. */
+int tcrt_plan_scene(const tcrt_scene* scene, int info[8], int grid_dims[3]);
 
 /* ---- render (replaces the pixel loop RayTracer.cpp:911-923) ----------------------- */
 /* Whole image -> host_rgb[width*height*3], x-major, z fastest, (r,g,b) float32: the layout

@@ -377,3 +377,66 @@ def test_txt_create_sizes_the_file_for_fixed_width_lines(tmp_path):
     with pytest.raises(api.TcrtError) as e:
         api.txt_create(p, str(tmp_path / "no_such_dir" / "x.txt"), 0.0)
     assert e.value.code == _ffi.TCRT_ERR_IO
+
+
+# ---- which pruning structures a scene gets (tcrt_plan_scene: the host half of tcrt_upload_scene, no device) ------------
+
+def _plan(name):
+    cam = api.Camera()
+    scene = api.Scene().build(name, cam)       # owns the arrays flatten() points into
+    return api.plan_scene(scene.flatten())
+
+
+def test_plan_scene_of_the_baseline_scenes():
+    """The structures behind the five BASELINE configs and the reference's SCENE 2: box clusters for the default scene's
+    24 rectangles, BVH + uniform grid in step with the lattice for the synthetic scenes (one cell per lattice site plus
+    the margin cells), BVH alone for SCENE 2 (its radius-10 sphere is 4x the median: no grid)."""
+    d = _plan("default")
+    assert (d["clusters"], d["cluster_rects"], d["bvh_spheres"], d["grid_cells"], d["linear_spheres"]) == (4, 24, 0, 0, 7)
+    s = _plan("synth256")
+    assert s["bvh_spheres"] == 256 and s["grid_dims"] == (9, 9, 5) and s["grid_cells"] == 405 and s["linear_spheres"] == 2
+    s = _plan("synth1024")
+    assert s["bvh_spheres"] == 1024 and s["grid_dims"] == (17, 17, 5) and s["linear_spheres"] == 2
+    t = _plan("two_mirrors")
+    assert t["bvh_spheres"] > 3900 and t["grid_cells"] == 0 and t["linear_finite"] == 4
+    assert all(v["staged_bytes"] <= 200 * 1024 for v in (d, s, t))
+
+
+_keep = []       # scenes own the arrays their flattened views point into
+
+
+def _sphere_scene(centres, radius):
+    s = api.Scene()
+    _keep.append(s)
+    s.addSphere((-2, -6, 12), .15).setAsLightSource(.75)
+    s.addInfinitePlane((0, 0, 0), (0, 0, 1), (1, 0, 0))
+    for c, r in zip(centres, radius):
+        s.addSphere(tuple(float(x) for x in c), float(r))
+    return s.flatten()
+
+
+def test_plan_scene_grid_acceptance_rules():
+    """tcrt_build_sphere_grid takes lattice-like sets only: at least 24 similar spheres; one sphere four times the median,
+    or spheres so crowded that a cell would hold more than 24, and the BVH stays alone."""
+    lattice = [(1.5 * i, 1.5 * j, .6 + 1.5 * k) for k in range(2) for j in range(4) for i in range(4)]      # 32 sites
+    ok = api.plan_scene(_sphere_scene(lattice, [.5] * 32))
+    assert ok["grid_cells"] > 0 and ok["bvh_spheres"] == 32 and min(ok["grid_dims"]) >= 2
+    few = api.plan_scene(_sphere_scene(lattice[:20], [.5] * 20))
+    assert few["grid_cells"] == 0
+    giant = api.plan_scene(_sphere_scene(lattice + [(40, 40, 12)], [.5] * 32 + [11.0]))
+    assert giant["grid_cells"] == 0 and giant["bvh_spheres"] == 33
+    rng = np.random.default_rng(5)
+    heap = [(3 + .02 * rng.random(), 3 + .02 * rng.random(), 1 + .02 * rng.random()) for _ in range(60)]     # 60 nearly coincident
+    crowded = api.plan_scene(_sphere_scene(heap, [.5] * 60))
+    assert crowded["grid_cells"] == 0
+    jitter = [(x + .3 * rng.random(), y + .3 * rng.random(), z + .3 * rng.random()) for x, y, z in lattice]
+    j = api.plan_scene(_sphere_scene(jitter, list(.4 + .2 * rng.random(32))))
+    assert j["grid_cells"] > 0
+
+
+def test_plan_scene_rejects_what_upload_rejects():
+    flat = _sphere_scene([(0, 0, 1)], [.5])
+    flat.n_spheres += 1                       # counts no longer add up
+    with pytest.raises(api.TcrtError) as e:
+        api.plan_scene(flat)
+    assert e.value.code == _ffi.TCRT_ERR_INVALID

@@ -195,6 +195,23 @@ class RenderStats:
         )
 
 
+STRUCTURE_KEYS = ("bvh_spheres", "grid_cells", "bvh_finite", "clusters", "cluster_rects", "linear_spheres", "linear_finite",
+                  "staged_bytes")
+
+
+def plan_scene(flat) -> dict:
+    """The pruning structures tcrt_upload_scene would build for a flattened scene (tcrt_plan_scene: host work only,
+    no device); "grid_dims" = cells per axis of the sphere grid, (0, 0, 0) without one."""
+    lib = _ffi.load()
+    info, dims = (C.c_int * 8)(), (C.c_int * 3)()
+    rc = lib.tcrt_plan_scene(C.byref(flat), info, dims)
+    if rc != 0:
+        raise TcrtError(rc, (lib.tcrt_last_error(None) or b"").decode())
+    out = dict(zip(STRUCTURE_KEYS, (int(v) for v in info)))
+    out["grid_dims"] = tuple(int(v) for v in dims)
+    return out
+
+
 class HostBuffer:
     """Pinned host memory (tcrt_alloc_host) viewed as a numpy array."""
 
@@ -252,8 +269,7 @@ class Context:
         """Which pruning structures the uploaded scene got (tcrt_scene_structures)."""
         info = (C.c_int * 8)()
         self._ck(self._lib.tcrt_scene_structures(self._h, info))
-        keys = ("bvh_spheres", "grid_cells", "bvh_finite", "clusters", "cluster_rects", "linear_spheres", "linear_finite", "staged_bytes")
-        return dict(zip(keys, (int(v) for v in info)))
+        return dict(zip(STRUCTURE_KEYS, (int(v) for v in info)))
 
     def render(self, params: TcrtParams, x0: int = 0, x1: Optional[int] = None, out: Optional[np.ndarray] = None):
         """Render columns [x0,x1) to host memory; returns (array[x1-x0, H, 3] float32, RenderStats)."""

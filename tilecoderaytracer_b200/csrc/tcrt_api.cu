@@ -377,11 +377,20 @@ void tcrt_destroy(tcrt_ctx* ctx) {
 }
 
 // ---- scene upload -----------------------------------------------------------------------------
+// What tcrt_upload_scene makes of a (validated) scene, on the host alone: the device blob and its description.
+struct SceneBlob {
+    std::vector<float4> host;
+    DeviceScene ds{};
+    size_t off[9] = {};          // surface, material, normals, frame, tex, bvh_s, bvh_f, grid cells, grid items
+    bool grid = false, bvh_s = false, bvh_f = false;
+    std::string err;
+};
+static int plan_scene_blob(const tcrt_scene* s, SceneBlob& out);
+static int validate_scene(tcrt_ctx* ctx, const tcrt_scene* s);
 static int build_scene_blob(tcrt_ctx* ctx, const tcrt_scene* s);
 static int send_scene(tcrt_ctx* ctx, const tcrt_camera* cam);
 
-int tcrt_upload_scene(tcrt_ctx* ctx, const tcrt_scene* s, const tcrt_camera* cam) {
-    if (!ctx || !s || !cam) return fail(ctx, TCRT_ERR_INVALID, "null argument");
+static int validate_scene(tcrt_ctx* ctx, const tcrt_scene* s) {
     if (s->n_objects < 0 || s->n_spheres < 0 || s->n_fin_planes < 0 || s->n_inf_planes < 0 || s->n_lights < 0 ||
         s->n_textures < 0 || s->n_spheres + s->n_fin_planes + s->n_inf_planes != s->n_objects)
         return fail(ctx, TCRT_ERR_INVALID, "inconsistent scene counts");
@@ -396,6 +405,13 @@ int tcrt_upload_scene(tcrt_ctx* ctx, const tcrt_scene* s, const tcrt_camera* cam
         if (s->light_obj[i] < 0 || s->light_obj[i] >= n) return fail(ctx, TCRT_ERR_INVALID, "light_obj out of range");
     for (int i = 0; i < n; i++)
         if (s->obj_info[4 * i + 3] >= s->n_textures) return fail(ctx, TCRT_ERR_INVALID, "texture id out of range");
+    return TCRT_OK;
+}
+
+int tcrt_upload_scene(tcrt_ctx* ctx, const tcrt_scene* s, const tcrt_camera* cam) {
+    if (!ctx || !s || !cam) return fail(ctx, TCRT_ERR_INVALID, "null argument");
+    if (int rc = validate_scene(ctx, s)) return rc;
+    const int n = s->n_objects;
 
     // ---- has this very scene been uploaded before?  (a caller that re-sends an unchanged scene every frame —
     // bench.py's e2e leg does — pays a compare and the H2D copy, not the sort + BVH/cluster build again)
@@ -431,7 +447,7 @@ int tcrt_upload_scene(tcrt_ctx* ctx, const tcrt_scene* s, const tcrt_camera* cam
 }
 
 // Flattened scene -> the device blob (sweep arrays, winner-only tables, BVH, box clusters) in ctx->scene_stage.
-static int build_scene_blob(tcrt_ctx* ctx, const tcrt_scene* s) {
+static int plan_scene_blob(const tcrt_scene* s, SceneBlob& out) {
     const int n = s->n_objects;
     auto is_light = [&](int obj) { return s->obj_info[4 * obj + 2] != 0; };
     // per type: non-light primitives first (shadow sweeps stop there), lights last
@@ -602,11 +618,12 @@ static int build_scene_blob(tcrt_ctx* ctx, const tcrt_scene* s) {
     const int n_prims = ds.n_sph + ds.n_fin + ds.n_inf;
     ds.blob_f4 = ds.idx_off + (n_prims + 3) / 4;
     if (std::max(bvh_depth_s, bvh_depth_f) + 2 > TCRT_BVH_STACK)   // cannot happen below ~2^40 primitives (tcrt_bvh.cpp)
-        return fail(ctx, TCRT_ERR_UNSUPPORTED, "BVH depth %d exceeds the traversal stack", std::max(bvh_depth_s, bvh_depth_f));
+        return out.err = "BVH depth " + std::to_string(std::max(bvh_depth_s, bvh_depth_f)) + " exceeds the traversal stack", TCRT_ERR_UNSUPPORTED;
     ds.stage_off = ds.n_sph_bvh;   // BVH leaves read their spheres through L1
     if ((size_t)(ds.blob_f4 - ds.stage_off) * sizeof(float4) > tcrt_render_max_smem())
-        return fail(ctx, TCRT_ERR_UNSUPPORTED, "scene needs %zu B of shared memory per CTA (limit %zu)",
-                    (size_t)(ds.blob_f4 - ds.stage_off) * sizeof(float4), tcrt_render_max_smem());
+        return out.err = "scene needs " + std::to_string((size_t)(ds.blob_f4 - ds.stage_off) * sizeof(float4)) +
+                         " B of shared memory per CTA (limit " + std::to_string(tcrt_render_max_smem()) + ")",
+               TCRT_ERR_UNSUPPORTED;
 
     const size_t off_surface = (size_t)ds.blob_f4;
     const size_t off_material = off_surface + n;
@@ -734,6 +751,28 @@ static int build_scene_blob(tcrt_ctx* ctx, const tcrt_scene* s) {
         }
     }
 
+    out.ds = ds;
+    out.off[0] = off_surface;
+    out.off[1] = off_material;
+    out.off[2] = off_normals;
+    out.off[3] = off_frame;
+    out.off[4] = off_tex;
+    out.off[5] = off_bvh_s;
+    out.off[6] = off_bvh_f;
+    out.off[7] = off_grid_cells;
+    out.off[8] = off_grid_items;
+    out.grid = has_grid;
+    out.bvh_s = !bvh_s.empty();
+    out.bvh_f = !bvh_f.empty();
+    out.host.swap(host);
+    return TCRT_OK;
+}
+
+static int build_scene_blob(tcrt_ctx* ctx, const tcrt_scene* s) {
+    SceneBlob b;
+    const int rc = plan_scene_blob(s, b);
+    if (rc) return fail(ctx, rc, "%s", b.err.c_str());
+    const size_t total_f4 = b.host.size();
     // into the pinned staging buffer (once every device has finished reading the previous scene out of it)
     for (auto& d : ctx->devs) {
         CK(ctx, cudaSetDevice(d.dev));
@@ -746,22 +785,14 @@ static int build_scene_blob(tcrt_ctx* ctx, const tcrt_scene* s) {
         CK(ctx, cudaHostAlloc((void**)&ctx->scene_stage, total_f4 * sizeof(float4), cudaHostAllocPortable));
         ctx->scene_stage_cap = total_f4;
     }
-    memcpy(ctx->scene_stage, host.data(), total_f4 * sizeof(float4));
+    memcpy(ctx->scene_stage, b.host.data(), total_f4 * sizeof(float4));
     ctx->scene_total_f4 = total_f4;
-    ctx->n_objects = n;
-    ctx->scene_ds = ds;
-    ctx->scene_off[0] = off_surface;
-    ctx->scene_off[1] = off_material;
-    ctx->scene_off[2] = off_normals;
-    ctx->scene_off[3] = off_frame;
-    ctx->scene_off[4] = off_tex;
-    ctx->scene_off[5] = off_bvh_s;
-    ctx->scene_off[6] = off_bvh_f;
-    ctx->scene_off[7] = off_grid_cells;
-    ctx->scene_off[8] = off_grid_items;
-    ctx->scene_grid = has_grid;
-    ctx->scene_bvh_s = !bvh_s.empty();
-    ctx->scene_bvh_f = !bvh_f.empty();
+    ctx->n_objects = s->n_objects;
+    ctx->scene_ds = b.ds;
+    for (int k = 0; k < 9; k++) ctx->scene_off[k] = b.off[k];
+    ctx->scene_grid = b.grid;
+    ctx->scene_bvh_s = b.bvh_s;
+    ctx->scene_bvh_f = b.bvh_f;
     return TCRT_OK;
 }
 
@@ -1275,18 +1306,33 @@ int tcrt_fp32_peak(tcrt_ctx* ctx, double* unfused, double* fma, double* ms_each)
     return TCRT_OK;
 }
 
+static void fill_structures(const DeviceScene& ds, bool grid, bool bvh_s, bool bvh_f, int info[8]) {
+    info[0] = bvh_s ? ds.n_sph_bvh : 0;                                                  // spheres in the sphere BVH
+    info[1] = grid ? ds.grid_dims[0] * ds.grid_dims[1] * ds.grid_dims[2] : 0;            // cells of the sphere grid
+    info[2] = bvh_f ? ds.n_fin_bvh : 0;                                                  // finite planes in their BVH
+    info[3] = ds.n_clu;                                                                  // box clusters
+    info[4] = ds.n_arect;                                                                // rectangles owned by clusters
+    info[5] = ds.n_sph - (bvh_s ? ds.n_sph_bvh : 0);                                     // spheres swept linearly
+    info[6] = ds.n_fin - ds.n_arect - (bvh_f ? ds.n_fin_bvh : 0);                        // finite planes swept linearly
+    info[7] = (int)((size_t)(ds.blob_f4 - ds.stage_off) * sizeof(float4));               // bytes staged per CTA
+}
+
 int tcrt_scene_structures(tcrt_ctx* ctx, int info[8]) {
     if (!ctx || !info) return fail(ctx, TCRT_ERR_INVALID, "null argument");
     if (!ctx->has_scene) return fail(ctx, TCRT_ERR_NO_SCENE, "tcrt_upload_scene has not been called");
-    const DeviceScene& ds = ctx->scene_ds;
-    info[0] = ctx->scene_bvh_s ? ds.n_sph_bvh : 0;                                          // spheres in the sphere BVH
-    info[1] = ctx->scene_grid ? ds.grid_dims[0] * ds.grid_dims[1] * ds.grid_dims[2] : 0;     // cells of the sphere grid
-    info[2] = ctx->scene_bvh_f ? ds.n_fin_bvh : 0;                                          // finite planes in their BVH
-    info[3] = ds.n_clu;                                                                     // box clusters
-    info[4] = ds.n_arect;                                                                   // rectangles owned by clusters
-    info[5] = ds.n_sph - (ctx->scene_bvh_s ? ds.n_sph_bvh : 0);                             // spheres swept linearly
-    info[6] = ds.n_fin - ds.n_arect - (ctx->scene_bvh_f ? ds.n_fin_bvh : 0);                // finite planes swept linearly
-    info[7] = (int)((size_t)(ds.blob_f4 - ds.stage_off) * sizeof(float4));                  // bytes staged per CTA
+    fill_structures(ctx->scene_ds, ctx->scene_grid, ctx->scene_bvh_s, ctx->scene_bvh_f, info);
+    return TCRT_OK;
+}
+
+int tcrt_plan_scene(const tcrt_scene* s, int info[8], int grid_dims[3]) {
+    if (!s || !info) return fail(nullptr, TCRT_ERR_INVALID, "null argument");
+    if (int rc = validate_scene(nullptr, s)) return rc;
+    SceneBlob b;
+    const int rc = plan_scene_blob(s, b);
+    if (rc) return fail(nullptr, rc, "%s", b.err.c_str());
+    fill_structures(b.ds, b.grid, b.bvh_s, b.bvh_f, info);
+    if (grid_dims)
+        for (int k = 0; k < 3; k++) grid_dims[k] = b.grid ? b.ds.grid_dims[k] : 0;
     return TCRT_OK;
 }
 
