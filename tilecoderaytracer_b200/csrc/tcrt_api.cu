@@ -913,10 +913,14 @@ static int render_submit(tcrt_ctx* ctx, const tcrt_params* p, int x0, int x1, fl
                 const long long chunk_px = 512 * 1024;   // 128 K .. 512 K pixels per chunk measure the same
                 n_chunks = (int)std::min<long long>(std::min<long long>(kMaxChunks, d.fr().x1 - d.fr().x0), std::max<long long>(1, px / chunk_px));
             }
-            // chunk boundaries on tile boundaries, so that every chunk of a tileable band is tileable
+            // chunk boundaries on tile boundaries, so that every chunk of a tileable band is tileable.  With the full
+            // number of chunks the first and the last ones are narrow: the copies start after the first chunk's kernel
+            // and the frame ends with the last chunk's copy, neither of which anything hides.
+            static const int kChunkWeight[kMaxChunks + 1] = {0, 1, 2, 4, 8, 12, 16, 20, 24, 28, 32, 36, 40, 42, 44, 45, 46};
             auto chunk_start = [&](int j) {
                 const int w = d.fr().x1 - d.fr().x0;
-                int c = (int)((long long)w * j / n_chunks);
+                int c = n_chunks == kMaxChunks ? (int)((long long)w * kChunkWeight[j] / kChunkWeight[kMaxChunks])
+                                               : (int)((long long)w * j / n_chunks);
                 if (j < n_chunks && w % TCRT_TILE_W == 0) c -= c % TCRT_TILE_W;
                 return d.fr().x0 + c;
             };
