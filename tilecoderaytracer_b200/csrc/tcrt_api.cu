@@ -910,7 +910,9 @@ static int render_submit(tcrt_ctx* ctx, const tcrt_params* p, int x0, int x1, fl
             int n_chunks = 1;
             if (host_band) {
                 const long long px = (long long)(d.fr().x1 - d.fr().x0) * p->height;
-                const long long chunk_px = 512 * 1024;   // 128 K .. 512 K pixels per chunk measure the same
+                // 256 K pixels (3 MB) or more per chunk: a 1080p frame is 7 chunks (0.56 ms end to end; 3 chunks 0.61 ms,
+                // 15 chunks 0.57 ms), larger frames kMaxChunks
+                const long long chunk_px = 256 * 1024;
                 n_chunks = (int)std::min<long long>(std::min<long long>(kMaxChunks, d.fr().x1 - d.fr().x0), std::max<long long>(1, px / chunk_px));
             }
             // chunk boundaries on tile boundaries, so that every chunk of a tileable band is tileable.  With the full
