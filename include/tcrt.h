@@ -175,7 +175,9 @@ int tcrt_plan_scene(const tcrt_scene* scene, int info[8], int grid_dims[3]);
 
 /* ---- render (replaces the pixel loop RayTracer.cpp:911-923) ----------------------- */
 /* Whole image -> host_rgb[width*height*3], x-major, z fastest, (r,g,b) float32: the layout
- * of the reference's pixels[W][H] (RayTracer.h:44).  stats may be NULL. */
+ * of the reference's pixels[W][H] (RayTracer.h:44).  stats may be NULL.  host_rgb may be pinned (tcrt_alloc_host,
+ * cudaHostAlloc: column chunks are copied straight into it while the next ones render) or pageable (a plain array:
+ * chunks pass through pinned staging and are copied on by worker threads of the ctx; about 15 % slower). */
 int tcrt_render(tcrt_ctx* ctx, const tcrt_params* params, float* host_rgb, tcrt_stats* stats);
 /* Columns [x0,x1) only -> host_rgb_band[(x1-x0)*height*3].  This is what one rank of a
  * one-process-per-GPU launch calls for its band. */
