@@ -1200,6 +1200,22 @@ int tcrt_wait(tcrt_ctx* ctx, int ticket, tcrt_stats* stats) {
 int tcrt_download(tcrt_ctx* ctx, float* host_band) {
     if (!ctx || !host_band) return fail(ctx, TCRT_ERR_INVALID, "null argument");
     if (!ctx->has_frame) return fail(ctx, TCRT_ERR_NO_FRAME, "nothing rendered yet");
+    // a large pageable destination: through pinned staging and the ctx's copy workers, like tcrt_render (render_impl)
+    if ((long long)(ctx->frame_x1 - ctx->frame_x0) * ctx->frame_h >= 512 * 1024) {
+        cudaPointerAttributes at{};
+        bool pageable;
+        if (cudaPointerGetAttributes(&at, host_band) != cudaSuccess) {
+            cudaGetLastError();
+            pageable = true;
+        } else {
+            pageable = at.type == cudaMemoryTypeUnregistered;
+        }
+        if (pageable) {
+            tcrt_params p{};
+            p.height = ctx->frame_h;
+            return copy_out_staged(ctx, &p, ctx->frame_x0, host_band);
+        }
+    }
     for (auto& d : ctx->devs) {
         if (d.fr().x1 <= d.fr().x0) continue;
         CK(ctx, cudaSetDevice(d.dev));
@@ -1812,10 +1828,14 @@ static int copy_out_staged(tcrt_ctx* ctx, const tcrt_params* p, int x0, float* h
         std::atomic<int> left[kTxtSlots];
         for (auto& l : left) l.store(0);
         size_t piece = 0;
-        for (int k = 0; k < f.n_chunks && e == cudaSuccess; k++) {
-            const size_t c0 = (size_t)(f.chunk_x[k] - f.x0) * p->height * 12, c1 = (size_t)(f.chunk_x[k + 1] - f.x0) * p->height * 12;
+        // chunk k may leave once its kernel has finished (a frame that is already complete — tcrt_download — has no chunk
+        // events of its own: older ones have long completed, and the render call has waited for the frame)
+        const int n_chunks = std::max(1, f.n_chunks);
+        for (int k = 0; k < n_chunks && e == cudaSuccess; k++) {
+            const int cx0 = f.n_chunks ? f.chunk_x[k] : f.x0, cx1 = f.n_chunks ? f.chunk_x[k + 1] : f.x1;
+            const size_t c0 = (size_t)(cx0 - f.x0) * p->height * 12, c1 = (size_t)(cx1 - f.x0) * p->height * 12;
             if (c1 <= c0) continue;
-            e = cudaStreamWaitEvent(d.copy_stream, f.ev_chunk[k], 0);
+            if (f.n_chunks > 1) e = cudaStreamWaitEvent(d.copy_stream, f.ev_chunk[k], 0);
             for (size_t b = c0; b < c1 && e == cudaSuccess; b += slot_bytes, piece++) {
                 const int slot = (int)(piece % kTxtSlots);
                 const size_t n = std::min(slot_bytes, c1 - b);
