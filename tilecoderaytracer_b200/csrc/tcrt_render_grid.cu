@@ -111,10 +111,8 @@ __global__ void __launch_bounds__(kGridBlock, kGridMinBlocks) render_grid_kernel
             V3 rO = ln.O, rD = ln.D;
             float best = rl.far_dist;    // nearest: best distance so far; shadow: distance to the light
             bool want = active;
-            float4 lp = make_float4(0.f, 0.f, 0.f, 0.f), lc = lp;
             if (any) {
-                lp = sm.light[2 * (pass - 1)];
-                lc = sm.light[2 * (pass - 1) + 1];
+                const float4 lp = sm.light[2 * (pass - 1)];
                 // inShade (:743-752): dir = L - P, |dir|, Ray(P, dir) normalises with the same length
                 const V3 dir = xyz(lp) - P;
                 best = __fsqrt_rn(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
@@ -297,6 +295,9 @@ __global__ void __launch_bounds__(kGridBlock, kGridMinBlocks) render_grid_kernel
             } else if (shade && (!rl.shadows_on || (want && !found))) {
                 // ---- light pass - 1 reaches the hit (RayTracer.cpp:548-588); rD is the light ray ---------------------------------
                 // (a light whose answer did not matter adds nothing and leaves `local` as it is: skipping it is exact)
+                // intensity and colour are read here, not before the walk: nothing to keep in registers across it
+                const float4 lp = sm.light[2 * (pass - 1)];
+                const float4 lc = sm.light[2 * (pass - 1) + 1];
                 if (diffuse > 0.0f) {        // cosineShade (:654-701)
                     const float c = dot(n2, rD);
                     if (c > 0.0f) {
