@@ -172,6 +172,12 @@ int tcrt_scene_structures(tcrt_ctx* ctx, int info[8]);
  * grid; what tcrt_upload_scene does before its copy).  grid_dims (optional): cells per axis of the sphere grid, 0 0 0
  * without one.  TCRT_ERR_UNSUPPORTED for a scene tcrt_upload_scene would refuse. */
 int tcrt_plan_scene(const tcrt_scene* scene, int info[8], int grid_dims[3]);
+/* Host only, for tests of the grid's soundness: for each of n_points points (x, y, z), the object
+ * indices of the spheres registered in the cell of the sphere grid that contains it — objects[i*cap .. i*cap + cap),
+ * counts[i] of them (0 outside the grid's box).  TCRT_ERR_UNSUPPORTED when the scene gets no grid.  grid_margin
+ * (optional): the fattening up to which a ray may use the grid. */
+int tcrt_plan_grid_cells(const tcrt_scene* scene, const float* points, int n_points, int* objects, int cap, int* counts,
+                         float* grid_margin);
 
 /* ---- render (replaces the pixel loop RayTracer.cpp:911-923) ----------------------- */
 /* Whole image -> host_rgb[width*height*3], x-major, z fastest, (r,g,b) float32: the layout

@@ -440,3 +440,50 @@ def test_plan_scene_rejects_what_upload_rejects():
     with pytest.raises(api.TcrtError) as e:
         api.plan_scene(flat)
     assert e.value.code == _ffi.TCRT_ERR_INVALID
+
+
+def _grid_soundness(flat, spheres, seed):
+    """a sphere the reference hits at distance d is met inside the sphere fattened by at most
+    grid_margin, and that point must lie in a cell where the sphere is registered.  Checked for random points of every
+    sphere's volume and of its shell out to the margin.  spheres: [(object index, centre, radius)]."""
+    rng = np.random.default_rng(seed)
+    _, margin = api.plan_grid_cells(flat, [(0, 0, 0)])
+    assert margin > 0
+    pts, owner = [], []
+    for obj, c, r in spheres:
+        u = rng.normal(size=(24, 3))
+        u /= np.linalg.norm(u, axis=1, keepdims=True)
+        rad = np.concatenate([r * rng.random(8) ** (1 / 3), np.full(8, r), r + margin * rng.random(8)])
+        pts.append(np.asarray(c) + u * rad[:, None])
+        owner += [obj] * 24
+    cells, _ = api.plan_grid_cells(flat, np.concatenate(pts))
+    missing = [(o, i) for i, (o, reg) in enumerate(zip(owner, cells)) if o not in reg]
+    assert not missing, f"{len(missing)} of {len(owner)} points lie in a cell that does not list their sphere, e.g. {missing[:3]}"
+    return max(len(reg) for reg in cells)
+
+
+@pytest.mark.parametrize("name", ["synth256", "synth1024"])
+def test_sphere_grid_registers_every_sphere_wherever_it_can_be_hit(name):
+    cam = api.Camera()
+    scene = api.Scene().build(name, cam)
+    flat = scene.flatten()
+    n = flat.n_spheres
+    geom = np.ctypeslib.as_array(flat.sphere_geom, shape=(n, 4))
+    objs = np.ctypeslib.as_array(flat.sphere_obj, shape=(n,))
+    info = np.ctypeslib.as_array(flat.obj_info, shape=(flat.n_objects, 4))
+    spheres = [(int(o), g[:3].copy(), float(np.sqrt(g[3]))) for g, o in zip(geom, objs) if info[o, 2] == 0]
+    assert len(spheres) == api.plan_scene(flat)["bvh_spheres"]
+    assert _grid_soundness(flat, spheres, 11) == 1          # in step with the lattice: one sphere per cell
+
+
+def test_sphere_grid_soundness_on_jittered_lattices():
+    for seed in (1, 2, 3):
+        rng = np.random.default_rng(seed)
+        centres = [(1.5 * i + .5 * rng.random(), 1.5 * j + .5 * rng.random(), .8 + 1.5 * k + .5 * rng.random())
+                   for k in range(3) for j in range(5) for i in range(5)]
+        radii = list(.35 + .3 * rng.random(len(centres)))
+        flat = _sphere_scene(centres, radii)
+        assert api.plan_scene(flat)["grid_cells"] > 0
+        # objects: light 0, plane 1, spheres from 2 (see _sphere_scene)
+        spheres = [(2 + i, np.array(c), r) for i, (c, r) in enumerate(zip(centres, radii))]
+        assert _grid_soundness(flat, spheres, 100 + seed) >= 2      # spheres straddle cells here

@@ -212,6 +212,21 @@ def plan_scene(flat) -> dict:
     return out
 
 
+def plan_grid_cells(flat, points, cap: int = 32):
+    """For every row of points[n, 3]: the object indices registered in the grid cell that contains it (a list of sets),
+    and the grid's margin — tcrt_plan_grid_cells, host only."""
+    lib = _ffi.load()
+    pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)
+    objs = np.full((len(pts), cap), -1, dtype=np.int32)
+    counts = np.zeros(len(pts), dtype=np.int32)
+    margin = C.c_float(0.0)
+    rc = lib.tcrt_plan_grid_cells(C.byref(flat), pts.ctypes.data, len(pts), objs.ctypes.data, cap, counts.ctypes.data, C.byref(margin))
+    if rc != 0:
+        raise TcrtError(rc, (lib.tcrt_last_error(None) or b"").decode())
+    assert counts.max(initial=0) <= cap, "raise cap"
+    return [set(int(v) for v in objs[i, :counts[i]]) for i in range(len(pts))], float(margin.value)
+
+
 class HostBuffer:
     """Pinned host memory (tcrt_alloc_host) viewed as a numpy array."""
 

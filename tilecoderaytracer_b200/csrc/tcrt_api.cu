@@ -1385,6 +1385,46 @@ int tcrt_scene_structures(tcrt_ctx* ctx, int info[8]) {
     return TCRT_OK;
 }
 
+int tcrt_plan_grid_cells(const tcrt_scene* s, const float* points, int n_points, int* objects, int cap, int* counts,
+                         float* grid_margin) {
+    if (!s || !points || !counts || n_points < 0 || cap < 0 || (cap > 0 && !objects)) return fail(nullptr, TCRT_ERR_INVALID, "bad argument");
+    if (int rc = validate_scene(nullptr, s)) return rc;
+    SceneBlob b;
+    const int rc = plan_scene_blob(s, b);
+    if (rc) return fail(nullptr, rc, "%s", b.err.c_str());
+    if (!b.grid) return fail(nullptr, TCRT_ERR_UNSUPPORTED, "the scene gets no sphere grid");
+    const DeviceScene& ds = b.ds;
+    if (grid_margin) *grid_margin = ds.grid_margin;
+    const int* items = reinterpret_cast<const int*>(&b.host[b.off[8]]);
+    const int* idx = reinterpret_cast<const int*>(&b.host[ds.idx_off]);
+    for (int i = 0; i < n_points; i++) {
+        const float* point = points + 3 * (size_t)i;
+        int* out = objects + (size_t)i * cap;
+        counts[i] = 0;
+        int c[3];
+        bool inside = true;
+        for (int k = 0; k < 3; k++) {
+            inside = inside && point[k] >= ds.grid_lo[k] && point[k] <= ds.grid_hi[k];
+            // the kernel's own cell arithmetic (tcrt_render_grid.cu)
+            c[k] = std::min(ds.grid_dims[k] - 1, std::max(0, (int)floorf((point[k] - ds.grid_lo[k]) * ds.grid_inv_cell[k])));
+        }
+        if (!inside) continue;                                                          // outside the grid's box
+        const size_t cell = (size_t)c[0] + (size_t)ds.grid_dims[0] * ((size_t)c[1] + (size_t)ds.grid_dims[1] * c[2]);
+        const float4 g = b.host[b.off[7] + 2 * cell];
+        int meta[4];
+        memcpy(meta, &b.host[b.off[7] + 2 * cell + 1], sizeof meta);
+        int n = 0;
+        if (g.w > 0.0f) {               // an empty cell carries the unhittable sphere (r^2 = -1e30)
+            if (n < cap) out[n] = idx[meta[1]];
+            n++;
+            for (int j = 0; j < meta[0]; j++, n++)
+                if (n < cap) out[n] = idx[items[meta[2] + j]];
+        }
+        counts[i] = n;
+    }
+    return TCRT_OK;
+}
+
 int tcrt_plan_scene(const tcrt_scene* s, int info[8], int grid_dims[3]) {
     if (!s || !info) return fail(nullptr, TCRT_ERR_INVALID, "null argument");
     if (int rc = validate_scene(nullptr, s)) return rc;
