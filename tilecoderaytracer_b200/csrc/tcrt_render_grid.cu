@@ -3,7 +3,9 @@
 // same arithmetic, bit-identical results, same persistent-warp pixel queue); what differs:
 //   * spheres are found with a 3D-DDA through the grid (a step costs a third of a BVH node, a ray meets a sphere after a
 //     few cells), the BVH remains for rays whose origin is so far away that the reference's rounding accepts wide misses
-//     (grid_margin, tcrt_render_common.cuh);
+//     (grid_margin / grid_k2_max, tcrt_render_common.cuh).  A cell is a 32-byte record that carries its first sphere's
+//     geometry (an unhittable sphere when the cell is empty): the sphere test of the usual one-sphere cell starts after
+//     one round of loads instead of three dependent ones (cell -> item -> sphere);
 //   * ONE walk in the kernel.  A bounce needs three walks — the nearest hit of the ray, then one shadow ray per light —
 //     and the megakernel inlines a nearest-hit and an any-hit walk; with the grid's code next to the BVH fallback that made
 //     a bounce's instruction footprint larger than the 32 KB instruction cache (76 % hit rate, 40 % of the stall samples
