@@ -8,6 +8,7 @@
 """
 from __future__ import annotations
 
+import hashlib
 import os
 import shutil
 import subprocess
@@ -43,11 +44,33 @@ def _run(cmd: list[str], quiet: bool = False) -> None:
     subprocess.run(cmd, check=True)
 
 
-def _stale(target: str, sources: list[str]) -> bool:
+def _digest(sources: list[str], extra: str = "") -> str:
+    h = hashlib.sha256(extra.encode())
+    for s in sorted(sources):
+        h.update(os.path.relpath(s, ROOT).encode())
+        with open(s, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def _stale(target: str, sources: list[str], extra: str = "") -> bool:
+    """Is `target` older than what it is built from?  By CONTENT: the digest of the sources (and flags) a target was
+    built from sits next to it in <target>.srchash.  A repo snapshot copied to another machine does not keep
+    modification times, and a rebuild there for nothing costs a minute of every test run; without a digest file
+    (a target built by hand) modification times decide."""
     if not os.path.exists(target):
         return True
-    t = os.path.getmtime(target)
-    return any(os.path.getmtime(s) > t for s in sources)
+    try:
+        with open(target + ".srchash") as f:
+            return f.read().strip() != _digest(sources, extra)
+    except OSError:
+        t = os.path.getmtime(target)
+        return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _stamp(target: str, sources: list[str], extra: str = "") -> None:
+    with open(target + ".srchash", "w") as f:
+        f.write(_digest(sources, extra) + "\n")
 
 
 def _deps() -> list[str]:
@@ -64,7 +87,8 @@ def build_lib(force: bool = False, verbose_ptxas: bool = False, defines: tuple =
     """Compile libtcrt.so for sm_100a (cross-compiles without a GPU).  `defines`/`out` build a
     developer variant (e.g. ("TCRT_MIN_BLOCKS=3",) -> libtcrt_mb3.so) for A/B timing."""
     lib_path = out or LIB_PATH
-    if not force and not _stale(lib_path, _deps()):
+    flags = " ".join([*NVCC_FLAGS, *CXX_FLAGS, *defines])
+    if not force and not _stale(lib_path, _deps(), flags):
         return lib_path
     objdir = os.path.join(PKG, "build", os.path.basename(lib_path))
     os.makedirs(objdir, exist_ok=True)
@@ -83,16 +107,19 @@ def build_lib(force: bool = False, verbose_ptxas: bool = False, defines: tuple =
     # static cudart: the library has no run-time dependency beyond libcuda (the driver)
     _run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static",
           *objs, "-o", lib_path, "-lpthread"])
+    _stamp(lib_path, _deps(), flags)
     return lib_path
 
 
 def build_oracle(force: bool = False) -> str:
     src = os.path.join(ROOT, "oracle", "tcrt_oracle.c")
-    if not force and not _stale(ORACLE_LIB_PATH, [src, os.path.join(ROOT, "include", "tcrt.h")]):
+    deps = [src, os.path.join(ROOT, "include", "tcrt.h")]
+    if not force and not _stale(ORACLE_LIB_PATH, deps):
         return ORACLE_LIB_PATH
     os.makedirs(os.path.dirname(ORACLE_LIB_PATH), exist_ok=True)
     _run(["gcc", "-std=gnu11", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-Wall",
           src, "-o", ORACLE_LIB_PATH, "-lm"])
+    _stamp(ORACLE_LIB_PATH, deps)
     return ORACLE_LIB_PATH
 
 
@@ -105,6 +132,8 @@ def build_ref() -> bool:
     srcs = [script, os.path.join(ROOT, "oracle", "ref_harness.cpp"), os.path.join(ROOT, "scenes", "scene_builders.inc")]
     if have_ref and (_stale(ref_bin, srcs) or _stale(cnt_bin, srcs)):
         _run(["bash", script])
+        _stamp(ref_bin, srcs)
+        _stamp(cnt_bin, srcs)
     return os.path.exists(ref_bin) and os.path.exists(cnt_bin)
 
 
