@@ -31,7 +31,10 @@ namespace {
 // What one frame in flight owns on a device.  Two sets per device: tcrt_render_async renders frame n+1 into one
 // while frame n's band is still being copied out of the other.
 constexpr int kMaxChunks = 16;     // column chunks of a band that goes to host memory (= events per frame)
-constexpr int kChunkStreams = 4;   // streams their launches alternate on
+#ifndef TCRT_CHUNK_STREAMS
+#define TCRT_CHUNK_STREAMS 4
+#endif
+constexpr int kChunkStreams = TCRT_CHUNK_STREAMS;   // streams their launches alternate on
 
 struct FrameRes {
     float* frame = nullptr;                   // the band, (x1-x0)*height*3 floats, x-major
