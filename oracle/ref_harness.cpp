@@ -83,6 +83,10 @@ int main(int argc, char** argv) {
         unsigned int seed = 0; int n = 0;
         if (sscanf(scene_name + 7, "%u:%d", &seed, &n) != 2) { fprintf(stderr, "bad random spec\n"); return 2; }
         tcrt_scenes::build_random(my_scene, seed, n);
+    } else if (!strncmp(scene_name, "lattice:", 8)) {
+        unsigned int seed = 0; int n = 0;
+        if (sscanf(scene_name + 8, "%u:%d", &seed, &n) != 2) { fprintf(stderr, "bad lattice spec\n"); return 2; }
+        tcrt_scenes::build_lattice(my_scene, seed, n);
     } else if (!strncmp(scene_name, "boxes:", 6)) {
         unsigned int seed = 0; int n = 0;
         if (sscanf(scene_name + 6, "%u:%d", &seed, &n) != 2) { fprintf(stderr, "bad boxes spec\n"); return 2; }

@@ -730,6 +730,21 @@ def test_sphere_grid_edge_cases(gpu_ctx, case):
     check_counters(stats, cnt)
 
 
+@pytest.mark.parametrize("spec,w,h,d", [("lattice:1:4", 160, 128, 12), ("lattice:2:5", 128, 96, 8), ("lattice:3:3", 96, 80, 30),
+                                        ("lattice:4:6", 128, 96, 6), ("lattice:7:8", 96, 64, 10)])
+def test_named_lattice_scenes_take_the_grid_and_match_the_oracle(gpu_ctx, spec, w, h, d):
+    """The jittered lattices of scenes/scene_builders.inc (the oracle is pinned to the reference binary on the same
+    scenes, tests/test_oracle.py): touching and overlapping spheres, two or three lights, mirrors and diffuse-0 spheres."""
+    scene, cam = make_scene(spec)
+    p = api.default_params(w, h, d)
+    gpu_ctx.upload(scene, cam)
+    assert gpu_ctx.scene_structures()["grid_cells"] > 0
+    img, stats = gpu_ctx.render(p)
+    want, cnt = O.render(scene.flatten(), cam.export(), p)
+    assert_bit_identical(img, want, spec)
+    check_counters(stats, cnt)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,w,h,d", [("synth256", 1920, 1080, 10), ("default", 3840, 2160, 50), ("default", 1920, 1080, 5)])
 def test_chunked_host_render_equals_single_launch(gpu_ctx, name, w, h, d):

@@ -476,6 +476,21 @@ def test_sphere_grid_registers_every_sphere_wherever_it_can_be_hit(name):
     assert _grid_soundness(flat, spheres, 11) == 1          # in step with the lattice: one sphere per cell
 
 
+@pytest.mark.parametrize("spec", ["lattice:1:4", "lattice:2:5", "lattice:3:3", "lattice:4:6", "lattice:7:8"])
+def test_sphere_grid_soundness_on_named_lattice_scenes(spec):
+    cam = api.Camera()
+    scene = api.Scene().build(spec, cam)
+    flat = scene.flatten()
+    n = flat.n_spheres
+    geom = np.ctypeslib.as_array(flat.sphere_geom, shape=(n, 4))
+    objs = np.ctypeslib.as_array(flat.sphere_obj, shape=(n,))
+    info = np.ctypeslib.as_array(flat.obj_info, shape=(flat.n_objects, 4))
+    spheres = [(int(o), g[:3].copy(), float(np.sqrt(g[3]))) for g, o in zip(geom, objs) if info[o, 2] == 0]
+    plan = api.plan_scene(flat)
+    assert plan["grid_cells"] > 0 and plan["bvh_spheres"] == len(spheres)
+    _grid_soundness(flat, spheres, 7)
+
+
 def test_sphere_grid_soundness_on_jittered_lattices():
     for seed in (1, 2, 3):
         rng = np.random.default_rng(seed)

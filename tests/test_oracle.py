@@ -63,6 +63,8 @@ def test_oracle_txt_md5_other_configs(golden, key):
     ("random:11:60", 96, 80, 10), ("random:12:200", 64, 48, 6), ("random:13:15", 96, 80, 30),
     ("random:14:500", 48, 40, 4), ("boxes:1:6", 96, 80, 8), ("boxes:2:10", 80, 64, 20), ("boxes:5:0", 64, 48, 5),
     ("boxes:11:9", 72, 56, 15), ("boxes:12:4", 72, 56, 50), ("random:15:90", 72, 56, 25), ("random:16:7", 72, 56, 50),
+    # jittered lattices with touching / overlapping spheres (the scenes the uniform sphere grid takes)
+    ("lattice:1:4", 96, 80, 12), ("lattice:2:5", 80, 64, 8), ("lattice:3:3", 72, 56, 30), ("lattice:4:6", 64, 48, 6),
 ])
 def test_oracle_matches_reference_binary(scene, w, h, d):
     """The unmodified reference (calculatePixel & co. compiled from /root/reference/src)."""

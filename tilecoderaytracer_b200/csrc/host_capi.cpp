@@ -57,6 +57,13 @@ int tcrt_hscene_build(tcrt_hscene* s, tcrt_hcamera* c, const char* name) {
         tcrt_scenes::build_random(s->scene, seed, n);
         return TCRT_OK;
     }
+    if (!strncmp(name, "lattice:", 8)) {
+        unsigned int seed = 0;
+        int n = 0;
+        if (sscanf(name + 8, "%u:%d", &seed, &n) != 2 || n < 1 || n > 30) return TCRT_ERR_INVALID;
+        tcrt_scenes::build_lattice(s->scene, seed, n);
+        return TCRT_OK;
+    }
     if (!strncmp(name, "boxes:", 6)) {
         unsigned int seed = 0;
         int n = 0;
