@@ -502,3 +502,39 @@ def test_sphere_grid_soundness_on_jittered_lattices():
         # objects: light 0, plane 1, spheres from 2 (see _sphere_scene)
         spheres = [(2 + i, np.array(c), r) for i, (c, r) in enumerate(zip(centres, radii))]
         assert _grid_soundness(flat, spheres, 100 + seed) >= 2      # spheres straddle cells here
+
+
+def test_sphere_grid_soundness_fuzz():
+    """Anisotropic spacings, radius ratios up to 3.5, strong jitter, clumps: whatever tcrt_build_sphere_grid decides, a grid
+    it builds registers every sphere wherever it can be hit (and a set it refuses simply keeps the BVH)."""
+    rng = np.random.default_rng(2026)
+    built = 0
+    for trial in range(40):
+        nx, ny, nz = (int(v) for v in rng.integers(2, 7, size=3))
+        sp = rng.uniform(.6, 2.5, size=3)
+        r0 = float(rng.uniform(.15, .6) * sp.min())
+        ratio = float(rng.uniform(1.0, 3.5))
+        jitter = float(rng.uniform(0.0, .6))
+        centres, radii = [], []
+        for k in range(nz):
+            for j in range(ny):
+                for i in range(nx):
+                    c = np.array([i, j, k]) * sp + jitter * sp * (rng.random(3) - .5) + np.array([-3, -1, 3.0])
+                    centres.append(tuple(float(v) for v in c))
+                    radii.append(r0 * float(rng.uniform(1.0, ratio)))
+        if trial % 5 == 0:                       # a clump of near-coincident spheres inside the lattice
+            for _ in range(int(rng.integers(3, 12))):
+                centres.append(tuple(float(v) for v in np.array(centres[0]) + .05 * rng.random(3)))
+                radii.append(r0)
+        flat = _sphere_scene(centres, radii)
+        plan = api.plan_scene(flat)
+        assert plan["bvh_spheres"] + plan["linear_spheres"] == len(centres) + 1          # + the light
+        if plan["grid_cells"] == 0:
+            continue
+        built += 1
+        assert max(plan["grid_dims"]) <= 64
+        spheres = [(2 + i, np.array(c), r) for i, (c, r) in enumerate(zip(centres, radii))]
+        in_grid = spheres if plan["bvh_spheres"] == len(spheres) else None
+        if in_grid is not None:                  # every sphere is BVH- and therefore grid-covered
+            _grid_soundness(flat, in_grid, 1000 + trial)
+    assert built >= 10, f"only {built} of 40 sets got a grid: the fuzz no longer exercises the builder"
